@@ -1,0 +1,218 @@
+/*
+ * kernel_model.c -- sequential CPU model of the B200 kernel's *algorithm*
+ * (wfa-gpu_b200/csrc/wfa_kernels.cu), NOT of the reference.
+ *
+ * TEST INFRASTRUCTURE ONLY (same rules as wfagpu_oracle.c).  It exists so the
+ * re-designed data flow can be proven equal to the faithful restatement on the
+ * CPU, where there is no GPU:
+ *
+ *   - penalty-only step table (kind / half-width / decision-row offset),
+ *   - symmetric range [-n, n] with NULL guard cells instead of per-pair
+ *     re-initialisation, rings of depth A (M) and e+1 (I, D),
+ *   - "clean" source semantics (a source that does not exist reads as NULL;
+ *     the reference reads stale ring contents instead, which can never lie on
+ *     an optimal path -- see DESIGN.md "Why clean rings are exact"),
+ *   - 4 decision bit-planes per 32 diagonals instead of piggy-backed 32-bit
+ *     words + prev pointers, followed by a geometric traceback that emits the
+ *     same 2-bit op stream the reference's chain decodes to.
+ *
+ * tests/test_kernel_model.py checks (finished, distance, CIGAR) of this model
+ * against wfagpu_oracle.c over random pairs and penalty sets.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define KM_NULL (-32000)
+#define KM_KIND_NULL 0
+#define KM_KIND_M 1
+#define KM_KIND_MDI 2
+
+typedef struct {
+    int32_t n;        /* half width of the range after this step            */
+    uint32_t row_off; /* decision row offset, in u32 words, MDI steps only  */
+    uint8_t kind;
+} km_step_t;
+
+/* Host-side table construction; mirrors wfagpu_build_step_table() in
+ * wfa-gpu_b200/host/step_table.c.  Existence logic follows
+ * lib/kernels/sequence_alignment_kernel.cu:584-631 (it depends on the
+ * penalties only).  Returns d_end: scores 1 .. d_end-1 may be computed. */
+int km_build_steps(int x, int o, int e, int max_steps, int max_dist, km_step_t *tab, uint64_t *arena_words)
+{
+    uint8_t *exM = (uint8_t *)calloc((size_t)max_dist + 1, 1);
+    uint8_t *exI = (uint8_t *)calloc((size_t)max_dist + 1, 1);
+    int steps = 1, n = 0, d;
+    uint64_t off = 0;
+    exM[0] = 1;
+    tab[0].kind = KM_KIND_M; tab[0].n = 0; tab[0].row_off = 0;
+    for (d = 1; d < max_dist; d++) {
+        if (!(steps < max_steps - 1)) break;
+        int gap = 0, mx = 0;
+        if (d - o - e >= 0) gap = exM[d - o - e] || exI[d - e];
+        if (gap) mx = 1;
+        else if (d - x >= 0) mx = exM[d - x];
+        if (!gap && !mx) {
+            tab[d].kind = KM_KIND_NULL;
+        } else if (!gap) {
+            tab[d].kind = KM_KIND_M; exM[d] = 1;
+        } else {
+            tab[d].kind = KM_KIND_MDI; exM[d] = 1; exI[d] = 1;
+            n++; steps++;
+        }
+        tab[d].n = n;
+        tab[d].row_off = (uint32_t)off;
+        if (tab[d].kind == KM_KIND_MDI) off += 4u * (uint64_t)((2 * n + 1 + 31) / 32);
+    }
+    free(exM); free(exI);
+    if (arena_words) *arena_words = off;
+    return d;
+}
+
+static inline int km_code(char c) { return (c & 6) >> 1; }
+
+static int km_extend(const char *text, const char *pattern, int tlen, int plen, int k, int off)
+{
+    int v = off - k, h = off;
+    if (v > plen || h > tlen) return KM_NULL;
+    while (v < plen && h < tlen && km_code(pattern[v]) == km_code(text[h])) { v++; h++; off++; }
+    return off;
+}
+
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/*
+ * One pair.  ops_out receives the 2-bit ops NEWEST FIRST (traceback order),
+ * one per byte; *n_ops their count.  Returns 0, or -1 on capacity problems.
+ */
+int km_align_pair(const char *pattern, int plen, const char *text, int tlen,
+                  int x, int o, int e, const km_step_t *tab, int d_end, int n_cap,
+                  int with_bt, int *finished, int *distance,
+                  uint8_t *ops_out, int ops_cap, int *n_ops, long *cells_out)
+{
+    const int A = imax(o + e, x) + 1;
+    const int E1 = e + 1;
+    const int G = A;
+    const int C = n_cap + 2 * G + 2;         /* centre index */
+    const int W = 2 * C + 1;
+    int16_t *Mr = (int16_t *)malloc((size_t)A * W * sizeof(int16_t));
+    int16_t *Ir = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
+    int16_t *Dr = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
+    uint64_t arena_words = 0;
+    for (int d = 0; d < d_end; d++)
+        if (tab[d].kind == KM_KIND_MDI) arena_words = tab[d].row_off + 4u * (uint64_t)((2 * tab[d].n + 1 + 31) / 32);
+    uint32_t *arena = with_bt ? (uint32_t *)calloc(arena_words + 4, sizeof(uint32_t)) : NULL;
+    /* poison the rings: the kernel never clears them between pairs */
+    for (long i = 0; i < (long)A * W; i++) Mr[i] = 12345;
+    for (long i = 0; i < (long)E1 * W; i++) { Ir[i] = 12345; Dr[i] = 12345; }
+    long cells = 0;
+
+    /* pair prologue: NULL-fill every ring row over [-2G, 2G] */
+    for (int r = 0; r < A; r++) for (int k = -2 * G; k <= 2 * G; k++) Mr[r * W + C + k] = KM_NULL;
+    for (int r = 0; r < E1; r++) for (int k = -2 * G; k <= 2 * G; k++) { Ir[r * W + C + k] = KM_NULL; Dr[r * W + C + k] = KM_NULL; }
+    Mr[0 * W + C + 0] = (int16_t)km_extend(text, pattern, tlen, plen, 0, 0);
+
+    const int kt = tlen - plen;
+    int fin = 0, d = 0;
+    if (kt == 0 && Mr[C] == tlen) {
+        fin = 1;
+    } else {
+        for (d = 1; d < d_end; d++) {
+            const km_step_t st = tab[d];
+            const int n = st.n;
+            if (n > n_cap) break;                       /* ring capacity exceeded */
+            int16_t *Mc = Mr + (d % A) * W + C;
+            int16_t *Ic = Ir + (d % E1) * W + C;
+            int16_t *Dc = Dr + (d % E1) * W + C;
+            if (st.kind == KM_KIND_NULL) {
+                for (int k = -n - G; k <= n + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+                continue;
+            }
+            const int16_t *Mx = (d - x >= 0) ? Mr + ((d - x) % A) * W + C : NULL;
+            if (st.kind == KM_KIND_M) {
+                for (int k = -n - G; k <= n + G; k++) {
+                    Ic[k] = KM_NULL; Dc[k] = KM_NULL;
+                    if (k < -n || k > n) { Mc[k] = KM_NULL; continue; }
+                    int m = Mx[k] + 1;
+                    if (m >= 0) m = km_extend(text, pattern, tlen, plen, k, m);
+                    Mc[k] = (int16_t)m;
+                    cells++;
+                }
+            } else {
+                /* sources that do not exist read as NULL rows: by construction their
+                 * ring rows hold NULL over the whole range that can be touched. */
+                const int16_t *Mo = Mr + ((((d - o - e) % A) + A) % A) * W + C;
+                const int16_t *Ie = Ir + ((((d - e) % E1) + E1) % E1) * W + C;
+                const int16_t *De = Dr + ((((d - e) % E1) + E1) % E1) * W + C;
+                const int16_t *Mxx = Mr + ((((d - x) % A) + A) % A) * W + C;
+                uint32_t *row = with_bt ? arena + st.row_off : NULL;
+                for (int k = -n - G; k < -n; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+                for (int k = n + 1; k <= n + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+                for (int k = -n; k <= n; k++) {
+                    const int io = Mo[k - 1] + 1, ie = Ie[k - 1] + 1;
+                    const int pI = imax(io * 2, ie * 2 + 1);
+                    const int I = pI >> 1;
+                    const int dopen = Mo[k + 1], dext = De[k + 1];
+                    const int pD = imax(dopen * 2, dext * 2 + 1);
+                    const int D = pD >> 1;
+                    const int X = Mxx[k] + 1;
+                    const int pM = imax(imax(X * 4 + 2, D * 4 + 3), I * 4 + 1);
+                    int M = pM >> 2;
+                    const int mop = pM & 3;
+                    if (M >= 0) M = km_extend(text, pattern, tlen, plen, k, M);
+                    Ic[k] = (int16_t)I; Dc[k] = (int16_t)D; Mc[k] = (int16_t)M;
+                    if (with_bt) {
+                        const int idx = k + n, g = idx >> 5, b = idx & 31;
+                        if (pI & 1)  row[4 * g + 0] |= 1u << b;
+                        if (pD & 1)  row[4 * g + 1] |= 1u << b;
+                        if (mop & 1) row[4 * g + 2] |= 1u << b;
+                        if (mop & 2) row[4 * g + 3] |= 1u << b;
+                    }
+                    cells++;
+                }
+            }
+            if (kt >= -n && kt <= n && Mc[kt] == tlen) { fin = 1; break; }
+        }
+    }
+    *finished = fin;
+    *distance = fin ? d : 0;
+    if (cells_out) *cells_out = cells;
+    *n_ops = 0;
+
+    int rc = 0;
+    if (fin && with_bt) {
+        /* traceback: emits SUB for every M cell, INS/DEL for every I/D cell */
+        int cd = d, ck = kt, comp = 0, cnt = 0; /* comp: 0 M, 1 I, 2 D */
+        while (!(comp == 0 && cd == 0)) {
+            if (cd < 0 || cnt >= ops_cap) { rc = -1; break; }
+            const km_step_t st = tab[cd];
+            if (comp == 0) {
+                ops_out[cnt++] = 2;
+                if (st.kind == KM_KIND_M) { cd -= x; continue; }
+                const int idx = ck + st.n, g = idx >> 5, b = idx & 31;
+                const uint32_t *row = arena + st.row_off + 4 * g;
+                const int mop = (int)((row[2] >> b) & 1) | (int)(((row[3] >> b) & 1) << 1);
+                if (mop == 2) cd -= x;
+                else if (mop == 1) comp = 1;
+                else comp = 2;
+            } else {
+                const int idx = ck + st.n, g = idx >> 5, b = idx & 31;
+                const uint32_t *row = arena + st.row_off + 4 * g;
+                if (comp == 1) {
+                    ops_out[cnt++] = 1;
+                    const int ext = (int)((row[0] >> b) & 1);
+                    ck -= 1;
+                    if (ext) cd -= e; else { cd -= o + e; comp = 0; }
+                } else {
+                    ops_out[cnt++] = 3;
+                    const int ext = (int)((row[1] >> b) & 1);
+                    ck += 1;
+                    if (ext) cd -= e; else { cd -= o + e; comp = 0; }
+                }
+            }
+        }
+        *n_ops = cnt;
+    }
+    free(Mr); free(Ir); free(Dr); free(arena);
+    return rc;
+}
