@@ -1,0 +1,156 @@
+/*
+ * wfagpu_b200.h -- C-ABI between the C host code and the hand-written sm_100a
+ * CUDA layer (wfa-gpu_b200/csrc), plus the B200-specific extensions of the
+ * public API.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * This is the boundary a reference maintainer would bind instead of
+ * lib/sequence_packing.cuh:27-40 (pack_sequences_gpu_async) and
+ * lib/sequence_alignment.cuh:29-114 (the allocate_xxx / reset_xxx helpers,
+ * launch_alignments_async, launch_alignments_distance_async, copyInResults),
+ * see INTEGRATION.md.
+ */
+#ifndef WFAGPU_B200_H
+#define WFAGPU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "wfa_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------- step table --- */
+/* Per-score control record.  It depends on the penalties and the step budget
+ * only (the existence logic of lib/kernels/sequence_alignment_kernel.cu:584-631
+ * never looks at the sequences), so the host builds it once per launch. */
+#define WFAGPU_STEP_NULL 0u
+#define WFAGPU_STEP_M    1u
+#define WFAGPU_STEP_MDI  2u
+typedef struct {
+    uint32_t row_off; /* offset of this score's decision row, in 16-byte units */
+    uint16_t n;       /* half width of the diagonal range [-n, n] after this step */
+    uint16_t kind;    /* WFAGPU_STEP_*                                          */
+} wfagpu_step_t;
+
+/* Builds the table for scores 0 .. d_end-1 (returns d_end; tab may be NULL to
+ * size it).  `arena_units` receives the number of 16-byte decision units one
+ * alignment can write.  Budget rule = reference: MDI steps stop once
+ * steps >= max_steps-1 (sequence_alignment_kernel.cu:584, steps starts at 1). */
+int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist,
+                            wfagpu_step_t *tab, uint64_t *arena_units);
+
+/* ------------------------------------------------------- device batches --- */
+/* One pair as the device sees it (built by the host from sequence_pair_t). */
+typedef struct {
+    uint32_t p_ascii; /* byte offset of the pattern in the batch ASCII buffer */
+    uint32_t t_ascii;
+    uint32_t p_word;  /* u32 offset of the packed pattern in the packed buffer (multiple of 4) */
+    uint32_t t_word;
+    uint32_t plen;
+    uint32_t tlen;
+    uint32_t flags;   /* WFAGPU_PAIR_* (has_N written by the pack kernel)      */
+    uint32_t reserved;
+} wfagpu_pair_t;
+#define WFAGPU_PAIR_HAS_N 1u
+
+/* Per-pair result record written by the alignment kernels. */
+typedef struct {
+    int32_t distance;  /* score if finished                                     */
+    uint32_t status;   /* WFAGPU_ST_*                                           */
+    uint32_t ops_off;  /* u32 offset of the packed op stream in the ops pool    */
+    uint32_t n_ops;    /* number of 2-bit backtrace ops, stored newest first    */
+} wfagpu_pair_out_t;
+#define WFAGPU_ST_FINISHED   1u
+#define WFAGPU_ST_OVERBUDGET 2u /* needs a larger wavefront budget (re-dispatch) */
+#define WFAGPU_ST_NEEDS_ASCII 4u /* flagged by the packer: byte-compare kernel    */
+
+typedef struct wfagpu_device wfagpu_device_t; /* opaque: streams, buffers, arenas of one GPU */
+
+typedef struct {
+    int x, o, e;
+    int max_steps;   /* budget of the first pass (reference `max_error`)        */
+    int band;        /* <=0 exact                                               */
+    int band_width;  /* banded window width (reference threads_per_block)       */
+    int with_cigar;
+    int threads_hint;
+    int workers_hint;
+} wfagpu_plan_t;
+
+/* Statistics of the last batch (kernel times from CUDA events on the launch
+ * stream; counts of kernels launched). */
+typedef struct {
+    float ms_h2d, ms_pack, ms_align, ms_d2h, ms_total;
+    uint32_t launches;        /* kernels launched for this batch                */
+    uint32_t redispatched;    /* pairs that needed a larger budget              */
+    uint32_t ascii_pairs;     /* pairs routed to the byte-compare kernel        */
+    uint64_t cells;           /* wavefront cells computed (0 unless profiling)  */
+    uint64_t h2d_bytes, d2h_bytes;
+} wfagpu_batch_stats_t;
+
+/* Opens (or returns the cached) context of CUDA device `dev`. NULL on failure
+ * (message on stderr); never falls back to the CPU. */
+wfagpu_device_t *wfagpu_device_open(int dev);
+void wfagpu_device_close_all(void);
+
+/*
+ * Aligns one batch on one device.  `ascii` is the host buffer holding the
+ * batch's sequences (pairs[i].*_ascii are offsets into it), `ascii_bytes` its
+ * length.  Results: out[i] for every pair; `ops` receives the packed op
+ * streams (capacity ops_cap u32, *ops_used on return).  Blocking; the device
+ * context pipelines internally over its streams.  Returns 0 on success.
+ *
+ * If `resident` is non-zero the batch's sequences are already on the device
+ * from a previous wfagpu_device_upload() and no H2D happens in this call.
+ */
+int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *ascii, size_t ascii_bytes,
+                         const wfagpu_pair_t *pairs, size_t n);
+int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const wfagpu_plan_t *plan,
+                        int resident);
+int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wfagpu_pair_out_t *out,
+                           uint32_t **ops, size_t *ops_used, uint32_t *pair_flags);
+void wfagpu_device_last_stats(wfagpu_device_t *d, int slot, wfagpu_batch_stats_t *st);
+int wfagpu_device_sm_count(wfagpu_device_t *d);
+
+/* Pack kernel alone (tests, replaces prepare_pack_sequences_gpu +
+ * pack_sequences_gpu_async, lib/sequence_packing.cu:27-116): uploads, packs and
+ * returns the packed words (layout: word j = bases [8j, 8j+16), first base in
+ * bits 31:30, code (c&6)>>1) and the has_N flags. */
+int wfagpu_device_pack_only(wfagpu_device_t *d, const char *ascii, size_t ascii_bytes,
+                            wfagpu_pair_t *pairs, size_t n, uint32_t *packed_out,
+                            size_t packed_words);
+
+/* ------------------------------------------------------------ host side --- */
+/* CIGAR text from a packed op stream (newest op first, 16 ops per u32, op j
+ * of a word in bits 2j+1:2j).  Same text as utils/cigar.c:96-272 produces
+ * from the reference's backtrace chain.  Appends to `cigar`. */
+bool wfagpu_ops_to_cigar(const char *pattern, size_t plen, const char *text, size_t tlen,
+                         int distance, const uint32_t *ops, uint32_t n_ops, wfa_cigar_t *cigar);
+
+/* Device selection for launch_alignments*: "0", "0,1,2", "all", or a count
+ * ("n:4").  Default (NULL/unset): environment WFAGPU_DEVICES, else device 0. */
+void wfagpu_set_devices(const char *spec);
+
+/* Stats of the last launch_alignments* call (summed over batches/devices). */
+typedef struct {
+    double wall_s;
+    double gpu_align_ms;  /* sum of alignment-kernel time over batches (max over devices per batch not tracked) */
+    double gpu_pack_ms;
+    uint64_t launches;
+    uint64_t redispatched;
+    uint64_t ascii_pairs;
+    uint64_t h2d_bytes, d2h_bytes;
+    int devices;
+} wfagpu_run_stats_t;
+void wfagpu_last_run_stats(wfagpu_run_stats_t *st);
+
+/* Deterministic synthetic pairs (text uniform over ACGT, pattern =
+ * text with ceil(L*err) edits, each uniformly mismatch / 1-base deletion /
+ * 1-base insertion; splitmix64 seeded).  Appends n pairs to the aligner. */
+bool wfagpu_synth_add_pairs(wfagpu_aligner_t *aligner, uint64_t seed, size_t n, int length,
+                            double err_lo, double err_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,76 @@
+"""GPU parity: the CUDA path through the public C API vs the oracle (bit-exact
+scores and CIGAR text).  Needs a B200; run with -m gpu."""
+import pytest
+
+import wfagpu
+from util import synth_aligner, check_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def run(specs, pen, cigar, max_error=None, batch=None, seed=0xB2000000):
+    a = synth_aligner(specs, seed)
+    assert a.initialize_parameters(*pen)
+    a.options.compute_cigar = cigar
+    if max_error is not None:
+        a.options.max_error = max_error
+    if batch is not None:
+        a.set_batch_size(batch)
+    a.align()
+    return a
+
+
+@pytest.mark.parametrize("cigar", [False, True])
+def test_short_reads_150bp(oracle, cigar):
+    # BASELINE config 1 shape: 150 bp, 2 % error, x=2,o=3,e=1 (and 5 % for config 2)
+    a = run([(2000, 150, 0.02, 0.02), (2000, 150, 0.05, 0.05)], (2, 3, 1), cigar)
+    assert check_against_oracle(oracle, a, 2, 3, 1, a.options.max_error, cigar) == []
+
+
+@pytest.mark.parametrize("cigar", [False, True])
+def test_1kbp_10pct_with_redispatch(oracle, cigar):
+    # config 3 shape: default budget 300 leaves ~5 % of the pairs over budget -> GPU re-dispatch
+    a = run([(400, 1000, 0.10, 0.10)], (2, 3, 1), cigar)
+    assert a.options.max_error == 300
+    assert check_against_oracle(oracle, a, 2, 3, 1, 300, cigar) == []
+
+
+def test_10kbp_cigar(oracle):
+    # headline shape: 10 kbp, 5 % error, -e 3000, CIGAR
+    a = run([(64, 10000, 0.05, 0.05)], (2, 3, 1), True, max_error=3000)
+    assert check_against_oracle(oracle, a, 2, 3, 1, 3000, True) == []
+
+
+@pytest.mark.parametrize("pen", [(1, 2, 1), (3, 1, 4), (5, 3, 2), (4, 6, 2), (2, 10, 5), (3, 5, 2)])
+def test_penalty_sets(oracle, pen):
+    a = run([(200, 150, 0.05, 0.05), (60, 700, 0.08, 0.08), (100, 30, 0.3, 0.3)], pen, True, max_error=400)
+    assert check_against_oracle(oracle, a, *pen, 400, True) == []
+
+
+def test_multi_batch_matches_single_batch(oracle):
+    a = run([(1000, 200, 0.04, 0.04)], (2, 3, 1), True, batch=1000)
+    b = run([(1000, 200, 0.04, 0.04)], (2, 3, 1), True, batch=130)
+    assert a.errors() == b.errors()
+    assert a.cigars() == b.cigars()
+
+
+def test_edge_cases(oracle):
+    a = wfagpu.Aligner()
+    cases = [("ACGT", "ACGT"), ("A", "A"), ("A", "C"), ("", "ACGT"), ("ACGT", ""), ("", ""),
+             ("ACGTACGTACGT", "ACGT"), ("ACGT", "ACGTACGTACGTTTTT"), ("AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", "A"),
+             ("ACGTNACGT", "ACGTNACGT"), ("ACGTNACGT", "ACGTACGT"), ("acgtacgt", "ACGTACGT"),
+             ("ACGTRYACGT", "ACGTRYACGT")]
+    for p, t in cases:
+        assert a.add_sequences(p, t)
+    assert a.initialize_parameters(2, 3, 1)
+    a.options.compute_cigar = True
+    a.align()
+    for i, (p, t) in enumerate(cases):
+        if oracle.has_N(p) or oracle.has_N(t):
+            # the reference sends these to CPU WFA (byte equality): check score + CIGAR validity
+            sc = oracle.cigar_score(p, t, a.cigar(i), 2, 3, 1)
+            assert sc == a.error(i), (p, t, a.cigar(i))
+            continue
+        r = oracle.align(p, t, 2, 3, 1, 200)
+        assert r["finished"]
+        assert (a.error(i), a.cigar(i)) == (r["distance"], r["cigar"]), (p, t)

@@ -1,0 +1,597 @@
+/*
+ * device.cu -- per-GPU context behind the C-ABI of include/wfagpu_b200.h.
+ *
+ * Replaces the launch glue of the reference (lib/sequence_alignment.cu:31-470,
+ * lib/sequence_packing.cu:96-116 and the device half of lib/align.cu:42-481):
+ * buffers are grow-only and cached per device, nothing is memset per batch, the
+ * decision arenas are sized by the step table, over-budget pairs are
+ * re-dispatched on the GPU with a doubled wavefront budget and pairs with
+ * non-ACGT bytes run through the byte-compare kernel.  There is no CPU path.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "wfa_kernels.cuh"
+
+using namespace wfagpu;
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            fprintf(stderr, "[wfagpu] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_),        \
+                    __FILE__, __LINE__, cudaGetErrorString(e_));                                  \
+            return -1;                                                                            \
+        }                                                                                         \
+    } while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n, bool keep = false, cudaStream_t s = 0)
+    {
+        if (n <= cap) return 0;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T *np = nullptr;
+        CK(cudaMalloc(&np, ncap * sizeof(T)));
+        if (keep && p && cap) CK(cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        if (keep) CK(cudaStreamSynchronize(s));
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return 0;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T *np = nullptr;
+        CK(cudaMallocHost(&np, ncap * sizeof(T)));
+        if (p) cudaFreeHost(p);
+        p = np;
+        cap = ncap;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { CTR_QUEUE = 0, CTR_POOL = 1, CTR_RETRY = 2, CTR_ASCII = 3, CTR_WORDS = 8 };
+
+struct LaunchCfg {
+    int group_threads;   /* 32 = warp per pair */
+    int groups_per_cta;
+    int ctas;
+    int stages;
+    int n_cap;
+    int row_stride, center;
+    int seq_words;
+    size_t smem;
+    int A, E1, G;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf<char> ascii;
+    DevBuf<uint32_t> packed;
+    DevBuf<wfagpu_pair_t> pairs;
+    DevBuf<uint32_t> order, retry[2], ascii_list;
+    DevBuf<wfagpu_pair_out_t> out;
+    DevBuf<uint32_t> pool;
+    DevBuf<uint32_t> counters;
+    DevBuf<unsigned long long> cells;
+    DevBuf<uint4> arena;
+    DevBuf<uint32_t> scratch;
+    DevBuf<wfagpu_step_t> steps;
+    PinBuf<wfagpu_pair_t> h_pairs;
+    PinBuf<uint32_t> h_order;
+    PinBuf<wfagpu_pair_out_t> h_out;
+    PinBuf<uint32_t> h_pool;
+    PinBuf<uint32_t> h_counters;
+    PinBuf<unsigned long long> h_cells;
+    size_t n = 0;
+    size_t ascii_bytes = 0;
+    size_t packed_words = 0;
+    uint32_t max_len = 0;
+    wfagpu_plan_t plan{};
+    wfagpu_batch_stats_t stats{};
+    bool have_events = false;
+};
+
+} // namespace
+
+struct wfagpu_device {
+    int dev = 0;
+    cudaDeviceProp prop{};
+    Slot slots[2];
+    bool count_cells = false;
+    int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
+};
+
+static std::mutex g_mu;
+static std::vector<wfagpu_device *> g_devices;
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto *d : g_devices)
+        if (d->dev == dev) {
+            cudaSetDevice(dev);
+            return d;
+        }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || dev < 0 || dev >= count) {
+        fprintf(stderr, "[wfagpu] CUDA device %d is not available (%s); this library has no CPU fallback\n", dev,
+                e != cudaSuccess ? cudaGetErrorString(e) : "out of range");
+        return nullptr;
+    }
+    if (cudaSetDevice(dev) != cudaSuccess) return nullptr;
+    wfagpu_device *d = new wfagpu_device();
+    d->dev = dev;
+    if (cudaGetDeviceProperties(&d->prop, dev) != cudaSuccess) {
+        delete d;
+        return nullptr;
+    }
+    if (d->prop.major < 10) {
+        fprintf(stderr, "[wfagpu] device %d is sm_%d%d; this build carries sm_100a code only\n", dev, d->prop.major,
+                d->prop.minor);
+        delete d;
+        return nullptr;
+    }
+    for (auto &s : d->slots) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete d;
+            return nullptr;
+        }
+        for (auto &ev : s.ev) cudaEventCreate(&ev);
+    }
+    d->count_cells = env_int("WFAGPU_COUNT_CELLS", 0) != 0;
+    d->force_threads = env_int("WFAGPU_THREADS", 0);
+    d->force_stages = env_int("WFAGPU_STAGES", 0);
+    d->force_ctas_per_sm = env_int("WFAGPU_CTAS_PER_SM", 0);
+    d->force_warp = env_int("WFAGPU_WARP_KERNEL", -1);
+    g_devices.push_back(d);
+    return d;
+}
+
+extern "C" void wfagpu_device_close_all(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto *d : g_devices) {
+        cudaSetDevice(d->dev);
+        for (auto &s : d->slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.ascii.release(); s.packed.release(); s.pairs.release(); s.order.release();
+            s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
+            s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release();
+            s.scratch.release(); s.steps.release();
+            s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
+            s.h_counters.release(); s.h_cells.release();
+            for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        delete d;
+    }
+    g_devices.clear();
+}
+
+extern "C" int wfagpu_device_sm_count(wfagpu_device_t *d) { return d ? d->prop.multiProcessorCount : 0; }
+
+static inline uint32_t packed_words_for(uint32_t len) { return ((((len + 7u) >> 3) + 1u) + 3u) & ~3u; }
+
+extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *ascii, size_t ascii_bytes,
+                                    const wfagpu_pair_t *pairs, size_t n)
+{
+    if (!d || slot < 0 || slot > 1) return -1;
+    CK(cudaSetDevice(d->dev));
+    Slot &s = d->slots[slot];
+    s.n = n;
+    s.ascii_bytes = ascii_bytes;
+    memset(&s.stats, 0, sizeof(s.stats));
+    if (n == 0) return 0;
+    if (s.h_pairs.ensure(n) || s.h_order.ensure(n)) return -1;
+    /* packed layout + longest-first schedule */
+    size_t words = 0;
+    uint32_t max_len = 0;
+    for (size_t i = 0; i < n; ++i) {
+        wfagpu_pair_t p = pairs[i];
+        p.p_word = (uint32_t)words;
+        words += packed_words_for(p.plen);
+        p.t_word = (uint32_t)words;
+        words += packed_words_for(p.tlen);
+        p.flags = 0;
+        s.h_pairs.p[i] = p;
+        s.h_order.p[i] = (uint32_t)i;
+        max_len = std::max(max_len, std::max(p.plen, p.tlen));
+    }
+    if (words >= (1ull << 32)) {
+        fprintf(stderr, "[wfagpu] batch too large for 32-bit packed offsets; use a smaller batch_size\n");
+        return -1;
+    }
+    s.packed_words = words;
+    s.max_len = max_len;
+    {
+        const wfagpu_pair_t *hp = s.h_pairs.p;
+        std::stable_sort(s.h_order.p, s.h_order.p + n, [hp](uint32_t a, uint32_t b) {
+            return (uint64_t)hp[a].plen + hp[a].tlen > (uint64_t)hp[b].plen + hp[b].tlen;
+        });
+    }
+    if (s.ascii.ensure(ascii_bytes + 64) || s.packed.ensure(words + 16) || s.pairs.ensure(n) || s.order.ensure(n) ||
+        s.retry[0].ensure(n) || s.retry[1].ensure(n) || s.ascii_list.ensure(n) || s.out.ensure(n) ||
+        s.counters.ensure(CTR_WORDS) || s.h_counters.ensure(CTR_WORDS) || s.cells.ensure(1) || s.h_cells.ensure(1))
+        return -1;
+    CK(cudaEventRecord(s.ev[0], s.stream));
+    CK(cudaMemcpyAsync(s.ascii.p, ascii, ascii_bytes, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemsetAsync(s.ascii.p + ascii_bytes, 0, 64, s.stream));
+    CK(cudaMemcpyAsync(s.pairs.p, s.h_pairs.p, n * sizeof(wfagpu_pair_t), cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.order.p, s.h_order.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemsetAsync(s.counters.p, 0, CTR_WORDS * sizeof(uint32_t), s.stream));
+    CK(cudaMemsetAsync(s.cells.p, 0, sizeof(unsigned long long), s.stream));
+    CK(cudaEventRecord(s.ev[1], s.stream));
+    PackParams pp{s.ascii.p, s.packed.p, s.pairs.p, (uint32_t)n};
+    launch_pack(pp, s.stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s.ev[2], s.stream));
+    s.stats.launches += 1;
+    s.stats.h2d_bytes += ascii_bytes + n * (sizeof(wfagpu_pair_t) + sizeof(uint32_t));
+    s.have_events = true;
+    return 0;
+}
+
+/* Shared-memory / launch-shape policy (replaces available_shared_mem_per_block and
+ * the <<<num_workers, tpb>>> choice of lib/sequence_alignment.cu:81-108,211-330). */
+static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint32_t max_len, size_t n_items,
+                      bool ascii, LaunchCfg *c)
+{
+    const int A = std::max(o + e, x) + 1, E1 = e + 1, G = A;
+    const int rows = A + 2 * E1;
+    const size_t smem_max = d->prop.sharedMemPerBlockOptin;        /* 227 KB on B200 */
+    const size_t smem_sm = d->prop.sharedMemPerMultiprocessor;     /* 228 KB */
+    const int seq_words = (int)packed_words_for(max_len);
+    c->A = A; c->E1 = E1; c->G = G; c->seq_words = seq_words;
+
+    int n_want = std::max(1, max_steps);                            /* n never exceeds the MDI step count */
+    auto rs = [&](int ncap) { return 2 * (ncap + 2 * G + 1) + 2; };
+
+    bool warp = (rs(n_want) <= 400) && max_len <= 1024;
+    if (d->force_warp >= 0) warp = d->force_warp != 0;
+
+    if (warp) {
+        c->group_threads = 32;
+        c->groups_per_cta = 8;
+        c->stages = 2;
+        c->n_cap = n_want;
+        c->row_stride = rs(c->n_cap);
+        c->center = c->n_cap + 2 * G + 1;
+        c->smem = exact_smem_bytes(A, E1, c->row_stride, seq_words, c->groups_per_cta, c->stages);
+        while (c->smem > smem_max && c->groups_per_cta > 1) {
+            c->groups_per_cta >>= 1;
+            c->smem = exact_smem_bytes(A, E1, c->row_stride, seq_words, c->groups_per_cta, c->stages);
+        }
+        if (c->smem > smem_max) warp = false;
+    }
+    if (!warp) {
+        c->groups_per_cta = 1;
+        /* try to fit two CTAs per SM; fall back to one CTA with as many diagonals as fit */
+        int stages = 2;
+        int n_cap = n_want;
+        size_t smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
+        const size_t half = (smem_sm - 2 * 1024) / 2;
+        if (smem > half) {
+            size_t s1 = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, 1);
+            if (s1 <= half) { stages = 1; smem = s1; }
+        }
+        if (smem > smem_max) {
+            stages = 1;
+            smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
+            if (smem > smem_max) {
+                /* clamp the half width to what one CTA can hold */
+                const size_t fixed = exact_smem_bytes(A, E1, 0, seq_words, 1, stages);
+                if (fixed + (size_t)rows * rs(1) * 2 > smem_max) return -2; /* sequences alone do not fit */
+                const size_t per_n = (size_t)rows * 2 * 2;          /* bytes per unit of n_cap */
+                n_cap = (int)((smem_max - fixed - 64) / per_n) - 2 * G - 2;
+                if (n_cap < 1) return -2;
+                smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
+            }
+        }
+        if (d->force_stages) {
+            stages = d->force_stages;
+            smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
+            if (smem > smem_max) return -2;
+        }
+        c->stages = stages;
+        c->n_cap = n_cap;
+        c->row_stride = rs(n_cap);
+        c->center = n_cap + 2 * G + 1;
+        c->smem = smem;
+        const int width = 2 * n_cap + 1;
+        int t = 1024;
+        if (smem <= half) t = 512;            /* two CTAs per SM */
+        if (width <= 1024) t = std::min(t, 256);
+        if (width <= 384) t = std::min(t, 128);
+        if (d->force_threads) t = d->force_threads;
+        c->group_threads = t;
+    }
+    const int threads = warp ? 32 * c->groups_per_cta : c->group_threads;
+    int occ = exact_max_ctas_per_sm(c->group_threads, c->groups_per_cta, c->smem, ascii);
+    if (occ < 1) {
+        fprintf(stderr, "[wfagpu] kernel configuration does not fit (threads=%d smem=%zu)\n", threads, c->smem);
+        return -1;
+    }
+    if (d->force_ctas_per_sm) occ = std::min(occ, d->force_ctas_per_sm);
+    size_t ctas = (size_t)occ * d->prop.multiProcessorCount;
+    const size_t need = (n_items + c->groups_per_cta - 1) / c->groups_per_cta;
+    c->ctas = (int)std::max<size_t>(1, std::min(ctas, need));
+    return 0;
+}
+
+/* Launch one pass over `n_items` entries of `order_dev`. */
+static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int max_steps, const uint32_t *order_dev,
+                       size_t n_items, uint32_t *retry_dev, bool ascii, int *n_cap_out, int *d_end_out)
+{
+    LaunchCfg c{};
+    int rc = choose_cfg(d, plan.x, plan.o, plan.e, max_steps, s.max_len, n_items, ascii, &c);
+    if (rc) return rc;
+    /* step table */
+    const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);
+    std::vector<wfagpu_step_t> tab((size_t)max_dist + 1);
+    uint64_t arena_units = 0;
+    const int d_end = wfagpu_build_step_table(plan.x, plan.o, plan.e, std::min(max_steps, c.n_cap + 2), max_dist,
+                                              tab.data(), &arena_units);
+    if (s.steps.ensure((size_t)d_end + 1)) return -1;
+    CK(cudaMemcpyAsync(s.steps.p, tab.data(), (size_t)d_end * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
+    CK(cudaStreamSynchronize(s.stream)); /* tab is a host temporary */
+
+    const size_t groups = (size_t)c.ctas * c.groups_per_cta;
+    if (!plan.with_cigar) arena_units = 0;
+    const uint32_t scratch_words = plan.with_cigar ? (uint32_t)((2 * (size_t)d_end + 31) / 16 + 2) : 1;
+    if (s.arena.ensure(groups * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
+    /* op pool: worst case for this pass on top of what is already used */
+    uint32_t pool_used = 0;
+    CK(cudaMemcpyAsync(&pool_used, s.counters.p + CTR_POOL, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    const size_t pool_need = (size_t)pool_used + (plan.with_cigar ? n_items * (size_t)scratch_words : 0) + 16;
+    if (pool_need >= (1ull << 32)) {
+        fprintf(stderr, "[wfagpu] op pool exceeds 32-bit offsets; use a smaller batch_size\n");
+        return -1;
+    }
+    if (s.pool.ensure(pool_need, true, s.stream)) return -1;
+
+    CK(cudaMemsetAsync(s.counters.p + CTR_QUEUE, 0, sizeof(uint32_t), s.stream));
+    CK(cudaMemsetAsync(s.counters.p + CTR_RETRY, 0, sizeof(uint32_t), s.stream));
+
+    KernelParams kp{};
+    kp.packed = s.packed.p;
+    kp.ascii = s.ascii.p;
+    kp.pairs = s.pairs.p;
+    kp.order = order_dev;
+    kp.n_items = (uint32_t)n_items;
+    kp.queue = s.counters.p + CTR_QUEUE;
+    kp.steps = s.steps.p;
+    kp.d_end = d_end;
+    kp.n_cap = c.n_cap;
+    kp.x = plan.x; kp.o = plan.o; kp.e = plan.e;
+    kp.A = c.A; kp.E1 = c.E1; kp.G = c.G;
+    kp.row_stride = c.row_stride;
+    kp.center = c.center;
+    kp.seq_words = c.seq_words;
+    kp.with_bt = plan.with_cigar;
+    kp.stages = c.stages;
+    kp.arena = s.arena.p;
+    kp.arena_units = arena_units;
+    kp.ops_scratch = s.scratch.p;
+    kp.ops_scratch_words = scratch_words;
+    kp.ops_pool = s.pool.p;
+    kp.ops_pool_head = s.counters.p + CTR_POOL;
+    kp.ops_pool_words = (uint32_t)std::min<size_t>(s.pool.cap, 0xffffffffu);
+    kp.out = s.out.p;
+    kp.retry_list = retry_dev;
+    kp.retry_count = s.counters.p + CTR_RETRY;
+    kp.ascii_list = s.ascii_list.p;
+    kp.ascii_count = s.counters.p + CTR_ASCII;
+    kp.cells = d->count_cells ? s.cells.p : nullptr;
+    if (env_int("WFAGPU_VERBOSE", 0))
+        fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d arena=%.1f MB\n",
+                n_items, max_steps, c.n_cap, d_end, c.group_threads, c.groups_per_cta, c.ctas, c.stages, c.smem,
+                (int)ascii, groups * arena_units * 16.0 / 1e6);
+    cudaError_t e = launch_exact(kp, c.group_threads, c.groups_per_cta, c.ctas, c.smem, ascii, s.stream);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[wfagpu] alignment kernel launch failed: %s\n", cudaGetErrorString(e));
+        return -1;
+    }
+    s.stats.launches += 1;
+    *n_cap_out = c.n_cap;
+    *d_end_out = d_end;
+    return 0;
+}
+
+extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const wfagpu_plan_t *plan, int resident)
+{
+    (void)resident;
+    if (!d || slot < 0 || slot > 1 || !plan) return -1;
+    CK(cudaSetDevice(d->dev));
+    Slot &s = d->slots[slot];
+    if (n != s.n) return -1;
+    s.plan = *plan;
+    if (n == 0) return 0;
+    if (plan->band > 0) {
+        fprintf(stderr, "[wfagpu] banded kernels are not built yet\n");
+        return -3;
+    }
+    CK(cudaEventRecord(s.ev[3], s.stream));
+    int n_cap = 0, d_end = 0;
+    int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, &n_cap, &d_end);
+    if (rc) return rc;
+    CK(cudaEventRecord(s.ev[4], s.stream));
+    return 0;
+}
+
+extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wfagpu_pair_out_t *out, uint32_t **ops,
+                                      size_t *ops_used, uint32_t *pair_flags)
+{
+    if (!d || slot < 0 || slot > 1) return -1;
+    CK(cudaSetDevice(d->dev));
+    Slot &s = d->slots[slot];
+    if (n != s.n) return -1;
+    if (ops) *ops = nullptr;
+    if (ops_used) *ops_used = 0;
+    if (n == 0) return 0;
+    const wfagpu_plan_t plan = s.plan;
+
+    auto read_counters = [&]() -> int {
+        CK(cudaMemcpyAsync(s.h_counters.p, s.counters.p, CTR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        return 0;
+    };
+    if (read_counters()) return -1;
+
+    /* ---- re-dispatch tier: double the wavefront budget until everything finishes ---- */
+    auto redispatch = [&](bool ascii, int start_steps) -> int {
+        int cur = 0;
+        long long steps = start_steps;
+        uint32_t pending = s.h_counters.p[CTR_RETRY];
+        while (pending > 0) {
+            s.stats.redispatched += pending;
+            const long long next = std::max<long long>(steps * 2, 64);
+            if (next > 30000) {
+                fprintf(stderr, "[wfagpu] %u pairs need more than %lld wavefront steps; not supported yet\n", pending, steps);
+                return -4;
+            }
+            steps = next;
+            int n_cap = 0, d_end = 0;
+            int rc = launch_pass(d, s, plan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, &n_cap, &d_end);
+            if (rc) return rc;
+            if (read_counters()) return -1;
+            if (n_cap + 2 < steps && s.h_counters.p[CTR_RETRY] > 0) {
+                fprintf(stderr, "[wfagpu] %u pairs exceed the on-chip wavefront capacity (n_cap=%d); not supported yet\n",
+                        s.h_counters.p[CTR_RETRY], n_cap);
+                return -4;
+            }
+            pending = s.h_counters.p[CTR_RETRY];
+            cur ^= 1;
+        }
+        return 0;
+    };
+    int rc = redispatch(false, plan.max_steps);
+    if (rc) return rc;
+
+    /* ---- pairs with non-ACGT bytes: byte-compare kernel on the ASCII copy ---- */
+    const uint32_t n_ascii = s.h_counters.p[CTR_ASCII];
+    if (n_ascii > 0) {
+        s.stats.ascii_pairs = n_ascii;
+        int n_cap = 0, d_end = 0;
+        rc = launch_pass(d, s, plan, plan.max_steps, s.ascii_list.p, n_ascii, s.retry[0].p, true, &n_cap, &d_end);
+        if (rc) return rc;
+        if (read_counters()) return -1;
+        rc = redispatch(true, plan.max_steps);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(s.ev[5], s.stream));
+
+    /* ---- results back to the host ---- */
+    if (s.h_out.ensure(n)) return -1;
+    const uint32_t pool_used = s.h_counters.p[CTR_POOL];
+    if (s.h_pool.ensure((size_t)pool_used + 1)) return -1;
+    CK(cudaMemcpyAsync(s.h_out.p, s.out.p, n * sizeof(wfagpu_pair_out_t), cudaMemcpyDeviceToHost, s.stream));
+    if (pool_used)
+        CK(cudaMemcpyAsync(s.h_pool.p, s.pool.p, (size_t)pool_used * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    if (pair_flags) CK(cudaMemcpyAsync(s.h_pairs.p, s.pairs.p, n * sizeof(wfagpu_pair_t), cudaMemcpyDeviceToHost, s.stream));
+    if (d->count_cells) CK(cudaMemcpyAsync(s.h_cells.p, s.cells.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    memcpy(out, s.h_out.p, n * sizeof(wfagpu_pair_out_t));
+    if (pair_flags)
+        for (size_t i = 0; i < n; ++i) pair_flags[i] = s.h_pairs.p[i].flags;
+    if (ops) *ops = s.h_pool.p;
+    if (ops_used) *ops_used = pool_used;
+    s.stats.d2h_bytes += n * sizeof(wfagpu_pair_out_t) + (size_t)pool_used * 4;
+    if (d->count_cells) s.stats.cells = s.h_cells.p[0];
+    if (s.have_events) {
+        cudaEventElapsedTime(&s.stats.ms_h2d, s.ev[0], s.ev[1]);
+        cudaEventElapsedTime(&s.stats.ms_pack, s.ev[1], s.ev[2]);
+        cudaEventElapsedTime(&s.stats.ms_align, s.ev[3], s.ev[5]);
+        cudaEventElapsedTime(&s.stats.ms_total, s.ev[0], s.ev[5]);
+    }
+    return 0;
+}
+
+extern "C" void wfagpu_device_last_stats(wfagpu_device_t *d, int slot, wfagpu_batch_stats_t *st)
+{
+    if (!d || !st || slot < 0 || slot > 1) return;
+    *st = d->slots[slot].stats;
+}
+
+extern "C" int wfagpu_device_pack_only(wfagpu_device_t *d, const char *ascii, size_t ascii_bytes, wfagpu_pair_t *pairs,
+                                       size_t n, uint32_t *packed_out, size_t packed_words)
+{
+    if (!d) return -1;
+    if (wfagpu_device_upload(d, 0, ascii, ascii_bytes, pairs, n)) return -1;
+    Slot &s = d->slots[0];
+    CK(cudaStreamSynchronize(s.stream));
+    if (packed_words < s.packed_words) return -1;
+    CK(cudaMemcpy(packed_out, s.packed.p, s.packed_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pairs, s.pairs.p, n * sizeof(wfagpu_pair_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* utils/device_query.cu:27-54 equivalents                                   */
+extern "C" void get_num_cuda_devices(int *n)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
+    if (n) *n = c;
+}
+
+extern "C" char *get_cuda_dev_name(int dev)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return nullptr;
+    return strdup(prop.name);
+}
+
+extern "C" int get_cuda_SM_count(int dev)
+{
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return v;
+}
+
+extern "C" void get_cuda_capability(int dev, int *major, int *minor)
+{
+    int a = 0, b = 0;
+    cudaDeviceGetAttribute(&a, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major) *major = a;
+    if (minor) *minor = b;
+}

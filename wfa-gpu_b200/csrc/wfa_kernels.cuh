@@ -1,0 +1,81 @@
+/*
+ * wfa_kernels.cuh -- device code of the B200-native gap-affine WFA hot path.
+ *
+ * Kernels (all integer SIMT work; no tensor cores -- there is no contraction):
+ *   pack_kernel      ASCII -> 2-bit, one warp per sequence, 128-bit aligned loads
+ *                    (replaces lib/kernels/sequence_packing_kernel.cu:28-116)
+ *   wfa_exact_kernel M/I/D offset recurrence + extend + decision bit-planes +
+ *                    traceback, one CTA (or one warp) per pair, persistent,
+ *                    next pair prefetched with cp.async.bulk (TMA 1-D)
+ *                    (replaces lib/kernels/sequence_alignment_kernel.cu:355-688,
+ *                     lib/kernels/sequence_distance_kernel.cu:175-423 and the
+ *                     device half of utils/cigar.c / lib/align.cu's backtrace slabs)
+ *
+ * Semantics reproduced from the reference:
+ *   k = h - v, offset = h; NULL = -32000 (int16, drifts upward, stays < 0);
+ *   I = max(M[d-o-e][k-1], I[d-e][k-1]) + 1   ties: extend beats open
+ *   D = max(M[d-o-e][k+1], D[d-e][k+1])       ties: extend beats open
+ *   M = extend(max(M[d-x][k]+1, I, D))        ties: D beats X beats I
+ *   an M cell whose winning candidate is outside the sequences becomes NULL,
+ *   I/D offsets are not bounds-checked (common_alignment_kernels.cuh:38).
+ */
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "wfagpu_b200.h"
+
+namespace wfagpu {
+
+constexpr int kOffNull = -32000;
+constexpr uint32_t kInvalidIdx = 0xffffffffu;
+
+struct KernelParams {
+    /* inputs */
+    const uint32_t *packed;       /* packed sequences, overlapped 8-base stride words        */
+    const char *ascii;            /* batch ASCII (byte-compare kernel only)                  */
+    wfagpu_pair_t *pairs;
+    const uint32_t *order;        /* pair indices, longest first                             */
+    uint32_t n_items;             /* entries of `order`                                      */
+    uint32_t *queue;              /* atomic work-queue head                                  */
+    const wfagpu_step_t *steps;
+    int d_end;                    /* scores 1 .. d_end-1 may be computed                     */
+    int n_cap;                    /* largest half width the rings of this launch can hold    */
+    int x, o, e;
+    int A, E1, G;                 /* ring depths (M: A, I/D: E1) and guard width             */
+    int row_stride;               /* int16 elements per ring row                             */
+    int center;                   /* index of k = 0 inside a row                             */
+    int seq_words;                /* u32 capacity of one packed sequence buffer in smem      */
+    int with_bt;
+    int stages;                   /* 1 or 2 sequence buffers per group (2 = prefetch next pair) */
+    /* decision arena: one region per worker group */
+    uint4 *arena;
+    uint64_t arena_units;         /* uint4 units per group                                   */
+    uint32_t *ops_scratch;        /* per-group scratch for the traceback's op words          */
+    uint32_t ops_scratch_words;
+    /* outputs */
+    uint32_t *ops_pool;
+    uint32_t *ops_pool_head;      /* bump allocator                                          */
+    uint32_t ops_pool_words;
+    wfagpu_pair_out_t *out;
+    uint32_t *retry_list;         /* pairs that ran out of budget                            */
+    uint32_t *retry_count;
+    uint32_t *ascii_list;         /* pairs the packer flagged (byte-compare launch)          */
+    uint32_t *ascii_count;
+    unsigned long long *cells;    /* optional work counter (may be null)                     */
+};
+
+struct PackParams {
+    const char *ascii;
+    uint32_t *packed;
+    wfagpu_pair_t *pairs;
+    uint32_t n_pairs;
+};
+
+void launch_pack(const PackParams &p, cudaStream_t s);
+/* group_threads == 32 -> warp-per-pair variant; otherwise CTA-per-pair */
+cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
+                         size_t smem_bytes, bool ascii_extend, cudaStream_t s);
+size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages);
+int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend);
+
+} // namespace wfagpu

@@ -1,0 +1,163 @@
+/*
+ * aligner.c -- the wfagpu_* public API (replaces lib/aligner.c:24-263).
+ *
+ * Same observable behaviour as the reference: sequences are copied into one
+ * growing host buffer, each at a 4-byte aligned offset and followed by NULs;
+ * metadata slots grow in blocks; defaults come from
+ * wfagpu_set_default_options.  The reference's grow_* helpers store byte sizes
+ * in element-count fields (lib/aligner.c:62-70,103-111) and leave the new
+ * metadata tail uninitialised; here lengths are kept in their own units and new
+ * memory is zeroed.
+ */
+#include <stdio.h>
+#include <string.h>
+#include "wfagpu_b200.h"
+
+#define SEQ_BUF_CHUNK ((size_t)1 << 20)
+#define META_CHUNK ((size_t)10000)
+#define FIRST_CIGAR_LEN 50
+
+#define WARN(...) do { fprintf(stderr, "WARNING: "); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
+#define ERR(...) do { fprintf(stderr, "[!] ERROR: "); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
+
+extern bool wfagpu_last_launch_ok(void); /* driver.c */
+
+bool wfagpu_initialize_aligner(wfagpu_aligner_t *aligner)
+{
+    if (!aligner) { ERR("Invalid aligner."); return false; }
+    memset(aligner, 0, sizeof(*aligner));
+    aligner->last_sequence_pair_idx = -1;
+    aligner->sequences_buffer = (wfagpu_seqbuf_t *)calloc(SEQ_BUF_CHUNK, 1);
+    aligner->sequences_metadata = (sequence_pair_t *)calloc(META_CHUNK, sizeof(sequence_pair_t));
+    if (!aligner->sequences_buffer || !aligner->sequences_metadata) {
+        ERR("Can not initialize the aligner buffers.");
+        return false;
+    }
+    aligner->sequences_buffer_len = SEQ_BUF_CHUNK;
+    aligner->sequences_metadata_len = META_CHUNK;
+    return true;
+}
+
+static bool reserve_bytes(wfagpu_aligner_t *a, size_t need)
+{
+    if (need < a->sequences_buffer_len) return true;
+    size_t nlen = a->sequences_buffer_len;
+    /* geometric growth: the reference adds 1 MiB at a time, which is quadratic for GB inputs */
+    while (nlen <= need) nlen += (nlen / 2 > SEQ_BUF_CHUNK ? nlen / 2 : SEQ_BUF_CHUNK);
+    char *nb = (char *)realloc(a->sequences_buffer, nlen);
+    if (!nb) return false;
+    memset(nb + a->sequences_buffer_len, 0, nlen - a->sequences_buffer_len);
+    a->sequences_buffer = nb;
+    a->sequences_buffer_len = nlen;
+    return true;
+}
+
+static bool reserve_pairs(wfagpu_aligner_t *a, size_t need)
+{
+    if (need <= a->sequences_metadata_len) return true;
+    size_t nlen = a->sequences_metadata_len;
+    while (nlen < need) nlen += (nlen / 2 > META_CHUNK ? nlen / 2 : META_CHUNK);
+    sequence_pair_t *nm = (sequence_pair_t *)realloc(a->sequences_metadata, nlen * sizeof(sequence_pair_t));
+    if (!nm) return false;
+    memset(nm + a->sequences_metadata_len, 0, (nlen - a->sequences_metadata_len) * sizeof(sequence_pair_t));
+    a->sequences_metadata = nm;
+    a->sequences_metadata_len = nlen;
+    return true;
+}
+
+bool wfagpu_add_sequences(wfagpu_aligner_t *aligner, const char *query, const char *target)
+{
+    if (!aligner) { ERR("Invalid aligner."); return false; }
+    if (!query || !target) { ERR("Invalid sequence pointers."); return false; }
+    if (!aligner->sequences_buffer || !aligner->sequences_metadata) { ERR("Aligner is not initialized."); return false; }
+
+    size_t p_off = 0;
+    if (aligner->last_sequence_pair_idx >= 0) {
+        const sequence_pair_t *last = &aligner->sequences_metadata[aligner->last_sequence_pair_idx];
+        p_off = WFA_ALIGN_32_BITS(last->text_offset + last->text_len + 1);
+    }
+    const size_t plen = strnlen(query, MAX_SEQ_LEN);
+    const size_t tlen = strnlen(target, MAX_SEQ_LEN);
+    if (plen >= MAX_SEQ_LEN || tlen >= MAX_SEQ_LEN) {
+        WARN("Sequences must be shorter than %lu.", MAX_SEQ_LEN - 1);
+        return false;
+    }
+    const size_t t_off = WFA_ALIGN_32_BITS(p_off + plen + 1);
+    if (!reserve_bytes(aligner, WFA_ALIGN_32_BITS(t_off + tlen + 1) + 8)) {
+        ERR("Sequences do not fit in memory. Aborting.");
+        return false;
+    }
+    const size_t slot = (size_t)(aligner->last_sequence_pair_idx + 1);
+    if (!reserve_pairs(aligner, slot + 1)) {
+        ERR("Can not resize sequence metadata buffer. Aborting.");
+        return false;
+    }
+    memcpy(aligner->sequences_buffer + p_off, query, plen);
+    memcpy(aligner->sequences_buffer + t_off, target, tlen);
+    sequence_pair_t *m = &aligner->sequences_metadata[slot];
+    memset(m, 0, sizeof(*m));
+    m->pattern_offset = p_off;
+    m->pattern_len = (unsigned)plen;
+    m->text_offset = t_off;
+    m->text_len = (unsigned)tlen;
+    aligner->last_sequence_pair_idx++;
+    aligner->num_sequence_pairs++;
+    return true;
+}
+
+bool wfagpu_initialize_parameters(wfagpu_aligner_t *aligner, affine_penalties_t penalties)
+{
+    if (!aligner) { ERR("Invalid aligner."); return false; }
+    if (penalties.x < 0 || penalties.o < 0 || penalties.e < 0) { ERR("Penalties must be >= 0."); return false; }
+    if (penalties.x == 0 && penalties.o == 0 && penalties.e == 0) { ERR("All penalties can not be 0."); return false; }
+    if (aligner->num_sequence_pairs == 0 || !aligner->sequences_metadata) {
+        ERR("Add the sequences before initializing the parameters.");
+        return false;
+    }
+    wfagpu_set_default_options(&aligner->alignment_options, aligner->sequences_metadata, penalties,
+                               aligner->num_sequence_pairs);
+    if (aligner->results) destroy_wfa_results(aligner->results, aligner->num_sequence_pairs);
+    return initialize_wfa_results(&aligner->results, aligner->num_sequence_pairs, FIRST_CIGAR_LEN);
+}
+
+bool wfagpu_set_batch_size(wfagpu_aligner_t *aligner, size_t batch_size)
+{
+    if (!aligner) { ERR("Invalid aligner."); return false; }
+    if (batch_size > aligner->num_sequence_pairs) {
+        WARN("Batch size must be less or equal than the number of sequences. Setting batch size to %zu.",
+             aligner->num_sequence_pairs);
+        batch_size = aligner->num_sequence_pairs;
+    }
+    if (batch_size == 0) {
+        WARN("Batch size can not be zero. Setting batch size to %zu.", aligner->num_sequence_pairs);
+        batch_size = aligner->num_sequence_pairs;
+    }
+    aligner->alignment_options.batch_size = batch_size;
+    return true;
+}
+
+void wfagpu_destroy_aligner(wfagpu_aligner_t *aligner)
+{
+    if (!aligner) return;
+    free(aligner->sequences_buffer);
+    free(aligner->sequences_metadata);
+    if (aligner->results) destroy_wfa_results(aligner->results, aligner->num_sequence_pairs);
+    aligner->sequences_buffer = NULL;
+    aligner->sequences_metadata = NULL;
+    aligner->results = NULL;
+}
+
+bool wfagpu_align(wfagpu_aligner_t *aligner)
+{
+    if (!aligner) { ERR("Invalid aligner."); return false; }
+    if (!aligner->results || !aligner->sequences_metadata) { ERR("Aligner parameters are not initialized."); return false; }
+    if (aligner->alignment_options.compute_cigar) {
+        launch_alignments(aligner->sequences_buffer, aligner->sequences_buffer_len, aligner->sequences_metadata,
+                          aligner->results, aligner->alignment_options, false);
+    } else {
+        launch_alignments_distance(aligner->sequences_buffer, aligner->sequences_buffer_len,
+                                   aligner->sequences_metadata, aligner->results, aligner->alignment_options, false);
+    }
+    /* the reference always returns true here; a failed GPU launch is reported instead */
+    return wfagpu_last_launch_ok();
+}

@@ -1,0 +1,344 @@
+/*
+ * driver.c -- batch driver behind launch_alignments / launch_alignments_distance
+ * (replaces the host half of lib/align.cu:42-881 and utils/wfa_cpu.c:30-164).
+ *
+ * The pair range is cut into chunks of at most `batch_size` pairs.  Each
+ * selected GPU is driven by one host thread that owns two device slots: while
+ * the GPU aligns chunk c, the thread turns the op streams of chunk c-1 into
+ * CIGAR text.  Pairs are independent, so GPUs never exchange data (no NCCL):
+ * results are written straight into alignment_results[i], disjoint per chunk.
+ * There is no CPU alignment path: over-budget and non-ACGT pairs are finished
+ * on the GPU inside wfagpu_device_download().
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <string.h>
+#include <time.h>
+#include <omp.h>
+#include "wfagpu_b200.h"
+
+#define MAX_DEVICES 64
+
+static char g_device_spec[256] = "";
+static wfagpu_run_stats_t g_last_stats;
+static bool g_last_ok = true;
+
+void wfagpu_set_devices(const char *spec)
+{
+    if (!spec) { g_device_spec[0] = 0; return; }
+    strncpy(g_device_spec, spec, sizeof(g_device_spec) - 1);
+    g_device_spec[sizeof(g_device_spec) - 1] = 0;
+}
+
+void wfagpu_last_run_stats(wfagpu_run_stats_t *st) { if (st) *st = g_last_stats; }
+bool wfagpu_last_launch_ok(void) { return g_last_ok; }
+
+static int parse_devices(int *devs)
+{
+    const char *spec = g_device_spec[0] ? g_device_spec : getenv("WFAGPU_DEVICES");
+    int visible = 0;
+    get_num_cuda_devices(&visible);
+    int n = 0;
+    if (!spec || !*spec) { devs[0] = 0; return 1; }
+    if (!strcmp(spec, "all")) {
+        for (int i = 0; i < visible && i < MAX_DEVICES; ++i) devs[n++] = i;
+        return n ? n : 1;
+    }
+    if (!strncmp(spec, "n:", 2)) {
+        int want = atoi(spec + 2);
+        for (int i = 0; i < want && i < visible && i < MAX_DEVICES; ++i) devs[n++] = i;
+        if (!n) { devs[0] = 0; n = 1; }
+        return n;
+    }
+    const char *p = spec;
+    while (*p && n < MAX_DEVICES) {
+        char *end;
+        long v = strtol(p, &end, 10);
+        if (end == p) break;
+        devs[n++] = (int)v;
+        p = (*end == ',') ? end + 1 : end;
+    }
+    if (!n) { devs[0] = 0; n = 1; }
+    return n;
+}
+
+typedef struct {
+    /* job */
+    char *buf;
+    size_t buf_size;
+    sequence_pair_t *meta;
+    wfa_alignment_result_t *res;
+    wfa_alignment_options_t opt;
+    bool cigar;
+    size_t n, chunk;
+    size_t n_chunks;
+    size_t next_chunk;      /* guarded by mu */
+    pthread_mutex_t mu;
+    bool failed;
+    int decode_threads;
+    /* accumulated stats */
+    wfagpu_run_stats_t stats;
+} job_t;
+
+typedef struct {
+    job_t *job;
+    int dev;
+} worker_t;
+
+typedef struct {
+    size_t from, n;
+    bool active;
+    wfagpu_pair_t *pairs;
+    size_t pairs_cap;
+    wfagpu_pair_out_t *out;
+    size_t out_cap;
+} inflight_t;
+
+static bool take_chunk(job_t *j, size_t *from, size_t *n)
+{
+    bool ok = false;
+    pthread_mutex_lock(&j->mu);
+    if (!j->failed && j->next_chunk < j->n_chunks) {
+        *from = j->next_chunk * j->chunk;
+        *n = (*from + j->chunk <= j->n) ? j->chunk : j->n - *from;
+        j->next_chunk++;
+        ok = true;
+    }
+    pthread_mutex_unlock(&j->mu);
+    return ok;
+}
+
+static void fail_job(job_t *j)
+{
+    pthread_mutex_lock(&j->mu);
+    j->failed = true;
+    pthread_mutex_unlock(&j->mu);
+}
+
+static int submit(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f)
+{
+    const sequence_pair_t *m = j->meta + f->from;
+    const size_t base = m[0].pattern_offset;
+    const size_t last = m[f->n - 1].text_offset + m[f->n - 1].text_len + 1;
+    if (last < base || last > j->buf_size) {
+        fprintf(stderr, "[!] ERROR: Reading out of sequences buffer. Aborting.\n");
+        return -1;
+    }
+    const size_t bytes = last - base;
+    if (bytes >= ((size_t)1 << 32)) {
+        fprintf(stderr, "[!] ERROR: a batch of %zu pairs spans %zu bytes; lower the batch size (32-bit offsets).\n", f->n, bytes);
+        return -1;
+    }
+    if (f->pairs_cap < f->n) {
+        free(f->pairs);
+        f->pairs = (wfagpu_pair_t *)malloc(f->n * sizeof(wfagpu_pair_t));
+        f->pairs_cap = f->n;
+    }
+    if (f->out_cap < f->n) {
+        free(f->out);
+        f->out = (wfagpu_pair_out_t *)malloc(f->n * sizeof(wfagpu_pair_out_t));
+        f->out_cap = f->n;
+    }
+    if (!f->pairs || !f->out) return -1;
+    size_t words = 0;
+    for (size_t i = 0; i < f->n; ++i) {
+        wfagpu_pair_t *p = &f->pairs[i];
+        if (m[i].pattern_offset < base || m[i].text_offset < base ||
+            m[i].pattern_offset + m[i].pattern_len > last || m[i].text_offset + m[i].text_len > last) {
+            fprintf(stderr, "[!] ERROR: sequence metadata is not laid out in increasing offsets.\n");
+            return -1;
+        }
+        p->p_ascii = (uint32_t)(m[i].pattern_offset - base);
+        p->t_ascii = (uint32_t)(m[i].text_offset - base);
+        p->plen = m[i].pattern_len;
+        p->tlen = m[i].text_len;
+        p->p_word = p->t_word = 0;
+        p->flags = 0;
+        p->reserved = 0;
+        /* the reference rewrites the packed offsets of every batch (lib/align.cu:103-115, 363-377) */
+        j->meta[f->from + i].pattern_offset_packed = words * 4;
+        words += ((((size_t)p->plen + 7) >> 3) + 1 + 3) & ~(size_t)3;
+        j->meta[f->from + i].text_offset_packed = words * 4;
+        words += ((((size_t)p->tlen + 7) >> 3) + 1 + 3) & ~(size_t)3;
+    }
+    wfagpu_plan_t plan;
+    memset(&plan, 0, sizeof(plan));
+    plan.x = j->opt.penalties.x;
+    plan.o = j->opt.penalties.o;
+    plan.e = j->opt.penalties.e;
+    plan.max_steps = j->opt.max_error;
+    plan.band = j->opt.band;
+    plan.band_width = j->opt.threads_per_block;
+    plan.with_cigar = j->cigar;
+    plan.threads_hint = j->opt.threads_per_block;
+    plan.workers_hint = j->opt.num_workers;
+    if (wfagpu_device_upload(d, slot, j->buf + base, bytes, f->pairs, f->n)) return -1;
+    if (wfagpu_device_align(d, slot, f->n, &plan, 0)) return -1;
+    f->active = true;
+    return 0;
+}
+
+static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu_run_stats_t *acc)
+{
+    uint32_t *ops = NULL;
+    size_t ops_used = 0;
+    if (wfagpu_device_download(d, slot, f->n, f->out, &ops, &ops_used, NULL)) return -1;
+    f->active = false;
+    wfagpu_batch_stats_t bs;
+    wfagpu_device_last_stats(d, slot, &bs);
+    acc->gpu_align_ms += bs.ms_align;
+    acc->gpu_pack_ms += bs.ms_pack;
+    acc->launches += bs.launches;
+    acc->redispatched += bs.redispatched;
+    acc->ascii_pairs += bs.ascii_pairs;
+    acc->h2d_bytes += bs.h2d_bytes;
+    acc->d2h_bytes += bs.d2h_bytes;
+
+    const sequence_pair_t *m = j->meta + f->from;
+    wfa_alignment_result_t *res = j->res + f->from;
+    int bad = 0;
+    const int nthreads = j->decode_threads;
+    #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) reduction(+:bad) if (f->n > 256)
+    for (long i = 0; i < (long)f->n; ++i) {
+        const wfagpu_pair_out_t *o = &f->out[i];
+        if (!(o->status & WFAGPU_ST_FINISHED)) { bad++; continue; }
+        res[i].error = (unsigned int)o->distance;
+        if (j->cigar) {
+            if (!wfagpu_ops_to_cigar(j->buf + m[i].pattern_offset, m[i].pattern_len, j->buf + m[i].text_offset,
+                                     m[i].text_len, o->distance, ops + o->ops_off, o->n_ops, &res[i].cigar))
+                bad++;
+        }
+    }
+    if (bad) {
+        fprintf(stderr, "[!] ERROR: %d alignments of the batch starting at %zu were not completed on the GPU.\n", bad, f->from);
+        return -1;
+    }
+    return 0;
+}
+
+static void *worker_main(void *arg)
+{
+    worker_t *w = (worker_t *)arg;
+    job_t *j = w->job;
+    wfagpu_device_t *d = wfagpu_device_open(w->dev);
+    if (!d) { fail_job(j); return NULL; }
+    inflight_t fl[2];
+    memset(fl, 0, sizeof(fl));
+    wfagpu_run_stats_t acc;
+    memset(&acc, 0, sizeof(acc));
+    int slot = 0;
+    bool ok = true;
+    while (ok) {
+        size_t from, n;
+        const bool got = take_chunk(j, &from, &n);
+        if (got) {
+            fl[slot].from = from;
+            fl[slot].n = n;
+            if (submit(j, d, slot, &fl[slot])) { ok = false; break; }
+        }
+        const int other = slot ^ 1;
+        if (fl[other].active && collect(j, d, other, &fl[other], &acc)) { ok = false; break; }
+        if (!got) {
+            if (fl[slot].active && collect(j, d, slot, &fl[slot], &acc)) ok = false;
+            break;
+        }
+        slot = other;
+    }
+    if (!ok) fail_job(j);
+    for (int s = 0; s < 2; ++s) { free(fl[s].pairs); free(fl[s].out); }
+    pthread_mutex_lock(&j->mu);
+    j->stats.gpu_align_ms += acc.gpu_align_ms;
+    j->stats.gpu_pack_ms += acc.gpu_pack_ms;
+    j->stats.launches += acc.launches;
+    j->stats.redispatched += acc.redispatched;
+    j->stats.ascii_pairs += acc.ascii_pairs;
+    j->stats.h2d_bytes += acc.h2d_bytes;
+    j->stats.d2h_bytes += acc.d2h_bytes;
+    pthread_mutex_unlock(&j->mu);
+    return NULL;
+}
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_alignment_result_t *res,
+                    wfa_alignment_options_t opt, bool cigar, bool check)
+{
+    (void)check;
+    const double t0 = now_s();
+    memset(&g_last_stats, 0, sizeof(g_last_stats));
+    g_last_ok = false;
+    if (!buf || !meta || !res) { fprintf(stderr, "[!] ERROR: invalid buffers.\n"); return; }
+    if (opt.num_alignments == 0) { g_last_ok = true; return; }
+    if (opt.penalties.x < 1 || opt.penalties.e < 1 || opt.penalties.o < 0) {
+        /* x = 0 or e = 0 make a wavefront depend on itself; the reference reads
+         * half-written memory in that case (lib/kernels/sequence_alignment_kernel.cu:149-152) */
+        fprintf(stderr, "[!] ERROR: penalties must satisfy x >= 1, e >= 1, o >= 0.\n");
+        return;
+    }
+    int devs[MAX_DEVICES];
+    const int ndev = parse_devices(devs);
+
+    job_t job;
+    memset(&job, 0, sizeof(job));
+    job.buf = buf; job.buf_size = buf_size; job.meta = meta; job.res = res; job.opt = opt; job.cigar = cigar;
+    job.n = opt.num_alignments;
+    size_t chunk = opt.batch_size;
+    if (chunk == 0 || chunk > job.n) chunk = job.n;
+    if (ndev > 1) {
+        /* enough chunks for every GPU to get work and for the tail to balance */
+        const size_t per = (job.n + (size_t)ndev * 2 - 1) / ((size_t)ndev * 2);
+        if (per > 0 && per < chunk) chunk = per;
+    }
+    /* keep a chunk's ASCII below the 32-bit offset limit */
+    {
+        const size_t span = meta[job.n - 1].text_offset + meta[job.n - 1].text_len + 1 - meta[0].pattern_offset;
+        const size_t avg = span / job.n + 1;
+        const size_t max_pairs = ((size_t)3 << 30) / avg;
+        if (max_pairs > 0 && chunk > max_pairs) chunk = max_pairs;
+    }
+    job.chunk = chunk;
+    job.n_chunks = (job.n + chunk - 1) / chunk;
+    pthread_mutex_init(&job.mu, NULL);
+    int cores = omp_get_num_procs();
+    job.decode_threads = cores / ndev > 0 ? cores / ndev : 1;
+
+    const int nworkers = (size_t)ndev < job.n_chunks ? ndev : (int)job.n_chunks;
+    worker_t workers[MAX_DEVICES];
+    pthread_t th[MAX_DEVICES];
+    for (int i = 0; i < nworkers; ++i) { workers[i].job = &job; workers[i].dev = devs[i]; }
+    if (nworkers == 1) {
+        worker_main(&workers[0]);
+    } else {
+        for (int i = 0; i < nworkers; ++i) pthread_create(&th[i], NULL, worker_main, &workers[i]);
+        for (int i = 0; i < nworkers; ++i) pthread_join(th[i], NULL);
+    }
+    pthread_mutex_destroy(&job.mu);
+    g_last_stats = job.stats;
+    g_last_stats.devices = nworkers;
+    g_last_stats.wall_s = now_s() - t0;
+    g_last_ok = !job.failed;
+    if (job.failed) fprintf(stderr, "[!] ERROR: alignment failed on the GPU (no CPU fallback exists in this library).\n");
+}
+
+void launch_alignments(char *sequences_buffer, const size_t sequences_buffer_size,
+                       sequence_pair_t *const sequences_metadata,
+                       wfa_alignment_result_t *const alignment_results,
+                       wfa_alignment_options_t options, bool check_correctness)
+{
+    run_job(sequences_buffer, sequences_buffer_size, sequences_metadata, alignment_results, options, true,
+            check_correctness);
+}
+
+void launch_alignments_distance(char *sequences_buffer, const size_t sequences_buffer_size,
+                                sequence_pair_t *const sequences_metadata,
+                                wfa_alignment_result_t *const alignment_results,
+                                wfa_alignment_options_t options, bool check_correctness)
+{
+    run_job(sequences_buffer, sequences_buffer_size, sequences_metadata, alignment_results, options, false,
+            check_correctness);
+}

@@ -1,0 +1,210 @@
+"""Python (ctypes) binding of the B200-native WFA-GPU drop-in library.
+
+Mirrors the reference's C API one to one (lib/aligner.h:49-62): an `Aligner`
+owns a `wfagpu_aligner_t`, sequences are added with `add_sequences(query,
+target)`, `initialize_parameters(x, o, e)` sets the reference defaults, option
+fields are poked directly (`aligner.options.compute_cigar = True`), `align()`
+runs on the GPU.  There is no CPU path: without the CUDA library or a GPU the
+calls fail loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libwfagpu.so"))
+
+BAND_NONE = -1
+
+
+class AffinePenalties(C.Structure):
+    _fields_ = [("x", C.c_int), ("o", C.c_int), ("e", C.c_int)]
+
+
+class SequencePair(C.Structure):
+    _fields_ = [("text_offset", C.c_size_t), ("pattern_offset", C.c_size_t),
+                ("text_offset_packed", C.c_size_t), ("pattern_offset_packed", C.c_size_t),
+                ("text_len", C.c_uint), ("pattern_len", C.c_uint), ("has_N", C.c_bool)]
+
+
+class Cigar(C.Structure):
+    _fields_ = [("buffer", C.c_void_p), ("buffer_size", C.c_size_t), ("last_free_position", C.c_size_t)]
+
+
+class AlignmentResult(C.Structure):
+    _fields_ = [("error", C.c_uint), ("cigar", Cigar)]
+
+
+class AlignmentOptions(C.Structure):
+    _fields_ = [("max_error", C.c_int), ("threads_per_block", C.c_int), ("num_workers", C.c_int),
+                ("band", C.c_int), ("batch_size", C.c_size_t), ("num_alignments", C.c_size_t),
+                ("penalties", AffinePenalties), ("compute_cigar", C.c_bool)]
+
+
+class AlignerStruct(C.Structure):
+    _fields_ = [("sequences_buffer", C.c_void_p), ("sequences_buffer_len", C.c_size_t),
+                ("sequences_metadata", C.POINTER(SequencePair)), ("sequences_metadata_len", C.c_size_t),
+                ("num_sequence_pairs", C.c_size_t), ("results", C.POINTER(AlignmentResult)),
+                ("last_sequence_pair_idx", C.c_int64), ("alignment_options", AlignmentOptions)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [("wall_s", C.c_double), ("gpu_align_ms", C.c_double), ("gpu_pack_ms", C.c_double),
+                ("launches", C.c_uint64), ("redispatched", C.c_uint64), ("ascii_pairs", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("devices", C.c_int)]
+
+
+class Step(C.Structure):
+    _fields_ = [("row_off", C.c_uint32), ("n", C.c_uint16), ("kind", C.c_uint16)]
+
+
+class DevPair(C.Structure):
+    _fields_ = [("p_ascii", C.c_uint32), ("t_ascii", C.c_uint32), ("p_word", C.c_uint32), ("t_word", C.c_uint32),
+                ("plen", C.c_uint32), ("tlen", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+EXPORTS = [
+    "wfagpu_initialize_aligner", "wfagpu_add_sequences", "wfagpu_initialize_parameters",
+    "wfagpu_set_batch_size", "wfagpu_align", "wfagpu_destroy_aligner",
+    "launch_alignments", "launch_alignments_distance",
+    "initialize_wfa_results", "destroy_wfa_results", "insert_ops",
+    "get_num_cuda_devices", "get_cuda_dev_name", "get_cuda_SM_count", "get_cuda_capability",
+    "wfagpu_build_step_table", "wfagpu_device_open", "wfagpu_device_close_all", "wfagpu_device_upload",
+    "wfagpu_device_align", "wfagpu_device_download", "wfagpu_device_last_stats", "wfagpu_device_sm_count",
+    "wfagpu_device_pack_only", "wfagpu_ops_to_cigar", "wfagpu_set_devices", "wfagpu_last_run_stats",
+    "wfagpu_synth_add_pairs",
+]
+
+_lib = None
+
+
+def load():
+    """Load lib/libwfagpu.so (built by wfa-gpu_b200/Makefile). Raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make -C wfa-gpu_b200` "
+            "(this package has no CPU or PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    L.wfagpu_initialize_aligner.argtypes = [P(AlignerStruct)]
+    L.wfagpu_initialize_aligner.restype = C.c_bool
+    L.wfagpu_add_sequences.argtypes = [P(AlignerStruct), C.c_char_p, C.c_char_p]
+    L.wfagpu_add_sequences.restype = C.c_bool
+    L.wfagpu_initialize_parameters.argtypes = [P(AlignerStruct), AffinePenalties]
+    L.wfagpu_initialize_parameters.restype = C.c_bool
+    L.wfagpu_set_batch_size.argtypes = [P(AlignerStruct), C.c_size_t]
+    L.wfagpu_set_batch_size.restype = C.c_bool
+    L.wfagpu_align.argtypes = [P(AlignerStruct)]
+    L.wfagpu_align.restype = C.c_bool
+    L.wfagpu_destroy_aligner.argtypes = [P(AlignerStruct)]
+    L.wfagpu_destroy_aligner.restype = None
+    L.wfagpu_set_devices.argtypes = [C.c_char_p]
+    L.wfagpu_last_run_stats.argtypes = [P(RunStats)]
+    L.wfagpu_synth_add_pairs.argtypes = [P(AlignerStruct), C.c_uint64, C.c_size_t, C.c_int, C.c_double, C.c_double]
+    L.wfagpu_synth_add_pairs.restype = C.c_bool
+    L.wfagpu_build_step_table.argtypes = [C.c_int] * 5 + [P(Step), P(C.c_uint64)]
+    L.wfagpu_ops_to_cigar.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int,
+                                      P(C.c_uint32), C.c_uint32, P(Cigar)]
+    L.wfagpu_ops_to_cigar.restype = C.c_bool
+    L.initialize_wfa_results.argtypes = [P(P(AlignmentResult)), C.c_size_t, C.c_size_t]
+    L.initialize_wfa_results.restype = C.c_bool
+    L.destroy_wfa_results.argtypes = [P(AlignmentResult), C.c_size_t]
+    L.destroy_wfa_results.restype = C.c_bool
+    L.get_num_cuda_devices.argtypes = [P(C.c_int)]
+    L.get_cuda_SM_count.argtypes = [C.c_int]
+    L.get_cuda_dev_name.argtypes = [C.c_int]
+    L.get_cuda_dev_name.restype = C.c_void_p
+    L.wfagpu_device_open.argtypes = [C.c_int]
+    L.wfagpu_device_open.restype = C.c_void_p
+    L.wfagpu_device_pack_only.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, P(DevPair), C.c_size_t,
+                                          P(C.c_uint32), C.c_size_t]
+    _lib = L
+    return L
+
+
+def _b(s):
+    return s if isinstance(s, bytes) else s.encode()
+
+
+class Aligner:
+    """Drop-in counterpart of the reference's wfagpu_aligner_t workflow."""
+
+    def __init__(self):
+        self.L = load()
+        self.s = AlignerStruct()
+        if not self.L.wfagpu_initialize_aligner(C.byref(self.s)):
+            raise RuntimeError("wfagpu_initialize_aligner failed")
+        self._alive = True
+
+    # -- reference API -------------------------------------------------------
+    def add_sequences(self, query, target):
+        return bool(self.L.wfagpu_add_sequences(C.byref(self.s), _b(query), _b(target)))
+
+    def initialize_parameters(self, x, o, e):
+        return bool(self.L.wfagpu_initialize_parameters(C.byref(self.s), AffinePenalties(x, o, e)))
+
+    def set_batch_size(self, n):
+        return bool(self.L.wfagpu_set_batch_size(C.byref(self.s), n))
+
+    @property
+    def options(self):
+        return self.s.alignment_options
+
+    def align(self):
+        if not self.L.wfagpu_align(C.byref(self.s)):
+            raise RuntimeError("wfagpu_align failed (see stderr); there is no CPU fallback")
+        return True
+
+    def destroy(self):
+        if self._alive:
+            self.L.wfagpu_destroy_aligner(C.byref(self.s))
+            self._alive = False
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # -- conveniences ----------------------------------------------------------
+    @property
+    def num_pairs(self):
+        return self.s.num_sequence_pairs
+
+    def error(self, i):
+        return self.s.results[i].error
+
+    def cigar(self, i):
+        buf = self.s.results[i].cigar.buffer
+        return C.string_at(buf).decode() if buf else ""
+
+    def errors(self):
+        return [self.s.results[i].error for i in range(self.num_pairs)]
+
+    def cigars(self):
+        return [self.cigar(i) for i in range(self.num_pairs)]
+
+    def pair(self, i):
+        m = self.s.sequences_metadata[i]
+        base = self.s.sequences_buffer
+        p = C.string_at(base + m.pattern_offset, m.pattern_len)
+        t = C.string_at(base + m.text_offset, m.text_len)
+        return p.decode(), t.decode()
+
+    def add_synthetic(self, seed, n, length, err_lo, err_hi=None):
+        if err_hi is None:
+            err_hi = err_lo
+        ok = self.L.wfagpu_synth_add_pairs(C.byref(self.s), seed, n, length, err_lo, err_hi)
+        if not ok:
+            raise RuntimeError("wfagpu_synth_add_pairs failed")
+
+    def run_stats(self):
+        st = RunStats()
+        self.L.wfagpu_last_run_stats(C.byref(st))
+        return {k: getattr(st, k) for k, _ in RunStats._fields_}
+
+
+def set_devices(spec):
+    load().wfagpu_set_devices(_b(spec) if spec is not None else None)
