@@ -94,14 +94,17 @@ wfagpu_device_t *wfagpu_device_open(int dev);
 void wfagpu_device_close_all(void);
 
 /*
- * Aligns one batch on one device.  `ascii` is the host buffer holding the
- * batch's sequences (pairs[i].*_ascii are offsets into it), `ascii_bytes` its
- * length.  Results: out[i] for every pair; `ops` receives the packed op
- * streams (capacity ops_cap u32, *ops_used on return).  Blocking; the device
- * context pipelines internally over its streams.  Returns 0 on success.
- *
- * If `resident` is non-zero the batch's sequences are already on the device
- * from a previous wfagpu_device_upload() and no H2D happens in this call.
+ * One batch on one device, in three phases on the slot's own stream (two slots
+ * per device let the host overlap batch c+1's copies with batch c's kernels):
+ *   upload    H2D of the batch's ASCII (pairs[i].*_ascii are offsets into
+ *             `ascii`), pair descriptors and the longest-first schedule;
+ *   align     pack kernel + alignment kernel (+ traceback); may be repeated on a
+ *             resident batch; asynchronous;
+ *   download  waits, finishes over-budget / non-ACGT pairs on the GPU
+ *             (re-dispatch with a doubled budget, byte-compare kernel) and copies
+ *             out[i] and the packed op streams back (`*ops` points into pinned
+ *             memory owned by the slot, valid until the slot's next download).
+ * All return 0 on success; failures print to stderr -- there is no CPU path.
  */
 int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *ascii, size_t ascii_bytes,
                          const wfagpu_pair_t *pairs, size_t n);
@@ -109,8 +112,21 @@ int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const wfagpu_pla
                         int resident);
 int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wfagpu_pair_out_t *out,
                            uint32_t **ops, size_t *ops_used, uint32_t *pair_flags);
+/* Waits for the slot's stream; event-timed durations of the last pack and first
+ * alignment launch (milliseconds). */
+int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, float *ms_align);
 void wfagpu_device_last_stats(wfagpu_device_t *d, int slot, wfagpu_batch_stats_t *st);
+/* Page-locks a caller buffer (e.g. the aligner's sequence buffer) so that the
+ * H2D copies run as asynchronous DMA. */
+int wfagpu_host_register(void *ptr, size_t bytes);
+int wfagpu_host_unregister(void *ptr);
 int wfagpu_device_sm_count(wfagpu_device_t *d);
+
+/* Builds the device-side descriptors of pairs [from, from+n) of a host buffer
+ * (also rewrites their *_offset_packed like lib/align.cu:103-115). `base_out` /
+ * `bytes_out`: the slice of the buffer to hand to wfagpu_device_upload. */
+int wfagpu_pairs_from_metadata(sequence_pair_t *meta, size_t from, size_t n, size_t buf_size,
+                               wfagpu_pair_t *pairs, size_t *base_out, size_t *bytes_out);
 
 /* Pack kernel alone (tests, replaces prepare_pack_sequences_gpu +
  * pack_sequences_gpu_async, lib/sequence_packing.cu:27-116): uploads, packs and
@@ -143,6 +159,10 @@ typedef struct {
     int devices;
 } wfagpu_run_stats_t;
 void wfagpu_last_run_stats(wfagpu_run_stats_t *st);
+
+/* Clears errors and CIGAR text of a previous wfagpu_align (the reference, like
+ * this library, appends to results[i].cigar) so an aligner can be re-aligned. */
+void wfagpu_reset_results(wfagpu_aligner_t *aligner);
 
 /* Deterministic synthetic pairs (text uniform over ACGT, pattern =
  * text with ceil(L*err) edits, each uniformly mismatch / 1-base deletion /

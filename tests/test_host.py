@@ -1,0 +1,168 @@
+"""Host-side logic of the product library, no GPU needed: ABI layout, exported symbols,
+step table, CIGAR text generation, synthetic generator, API argument checking."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import wfagpu
+from oracle import KmStep
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = set()
+    for h in ("wfa_gpu.h", "wfagpu_b200.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"static inline[^{]*\{.*?\n\}", "", src, flags=re.S)
+        for m in re.finditer(r"\b([a-z_][a-zA-Z0-9_]*)\s*\([^;{]*\)\s*;", src):
+            declared.add(m.group(1))
+    declared -= {"defined", "sizeof"}
+    assert {"wfagpu_align", "launch_alignments", "wfagpu_device_align", "get_cuda_SM_count"} <= declared
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
+    for name in wfagpu.EXPORTS:
+        assert hasattr(lib, name)
+
+
+def test_struct_layout_matches_reference_abi():
+    # sizes/offsets measured on the reference headers (x86-64)
+    assert C.sizeof(wfagpu.AlignerStruct) == 104
+    assert wfagpu.AlignerStruct.alignment_options.offset == 56
+    assert wfagpu.AlignerStruct.last_sequence_pair_idx.offset == 48
+    assert C.sizeof(wfagpu.AlignmentOptions) == 48
+    assert wfagpu.AlignmentOptions.batch_size.offset == 16
+    assert wfagpu.AlignmentOptions.penalties.offset == 32
+    assert wfagpu.AlignmentOptions.compute_cigar.offset == 44
+    assert C.sizeof(wfagpu.AlignmentResult) == 32 and wfagpu.AlignmentResult.cigar.offset == 8
+    assert C.sizeof(wfagpu.SequencePair) == 48 and wfagpu.SequencePair.has_N.offset == 40
+    assert C.sizeof(wfagpu.AffinePenalties) == 12
+
+
+def test_c_header_layout_with_gcc(tmp_path):
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "include/wfa_gpu.h"\n#include <stddef.h>\n#include <stdio.h>\n'
+        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(wfagpu_aligner_t),"
+        "offsetof(wfagpu_aligner_t, alignment_options), sizeof(wfa_alignment_options_t),"
+        "offsetof(wfa_alignment_options_t, compute_cigar), sizeof(wfa_alignment_result_t),"
+        "sizeof(sequence_pair_t), sizeof(alignment_result_t), sizeof(wfa_backtrace_t));return 0;}\n")
+    exe = tmp_path / "abi"
+    assert os.system(f"gcc -I{ROOT} -o {exe} {src}") == 0
+    out = os.popen(str(exe)).read().split()
+    assert out == ["104", "56", "48", "44", "32", "48", "20", "8"]
+
+
+def test_api_argument_checks(lib):
+    # tests/test_api.c:30-57
+    assert not lib.wfagpu_initialize_aligner(None)
+    assert not lib.wfagpu_add_sequences(None, b"ACGT", b"ACGT")
+    assert not lib.wfagpu_initialize_parameters(None, wfagpu.AffinePenalties(2, 3, 1))
+    a = wfagpu.Aligner()
+    assert a.add_sequences("ACGT", "ACGA")
+    assert not a.initialize_parameters(-2, 3, 1)
+    assert not a.initialize_parameters(0, 0, 0)
+    assert a.initialize_parameters(2, 3, 1)
+    assert not a.add_sequences("A" * 32768, "ACGT")      # lib/aligner.c:139-142: max length 32767
+    assert a.add_sequences("A" * 32767, "ACGT")
+
+
+def test_buffer_layout_and_defaults():
+    a = wfagpu.Aligner()
+    seqs = [("ACG", "ACGT"), ("ACGTA", "AC"), ("", "A"), ("ACGTACGT", "ACGTACGA")]
+    for p, t in seqs:
+        assert a.add_sequences(p, t)
+    off = 0
+    for i, (p, t) in enumerate(seqs):
+        m = a.s.sequences_metadata[i]
+        assert m.pattern_offset == off and m.pattern_len == len(p)
+        off = (off + len(p) + 1) + (4 - (off + len(p) + 1) % 4)
+        assert m.text_offset == off and m.text_len == len(t)
+        off = (off + len(t) + 1) + (4 - (off + len(t) + 1) % 4)
+        assert a.pair(i) == (p, t)
+    b = wfagpu.Aligner()
+    b.add_synthetic(1, 25, 10000, 0.05)
+    assert b.initialize_parameters(2, 3, 1)
+    o = b.options
+    # lib/alignment_parameters.h:83-106: 0.1 * max(len) * max(x,o,e), tpb from the wavefront width
+    assert (o.max_error, o.threads_per_block, o.band, o.batch_size, o.compute_cigar) == (3000, 1024, -1, 2, False)
+    assert b.set_batch_size(0) and o.batch_size == 25
+    assert b.set_batch_size(99) and o.batch_size == 25
+
+
+@pytest.mark.parametrize("pen", [(2, 3, 1), (5, 3, 2), (4, 6, 2), (1, 2, 1), (3, 1, 4), (2, 10, 5)])
+def test_step_table_equals_model(lib, oracle, pen):
+    x, o, e = pen
+    ms = 300
+    md = ms * (max(x, o + e) + 1) + 16
+    t1 = (wfagpu.Step * (md + 1))(); u1 = C.c_uint64()
+    d1 = lib.wfagpu_build_step_table(x, o, e, ms, md, t1, C.byref(u1))
+    t2 = (KmStep * (md + 1))(); u2 = C.c_uint64()
+    d2 = oracle.L.km_build_steps(x, o, e, ms, md, t2, C.byref(u2))
+    assert d1 == d2 and u1.value * 4 == u2.value
+    for d in range(d1):
+        assert (t1[d].kind, t1[d].n) == (t2[d].kind, t2[d].n)
+        if t1[d].kind == 2:
+            assert t1[d].row_off * 4 == t2[d].row_off
+
+
+def _model_ops(oracle, p, t, pen, budget):
+    x, o, e = pen
+    pb, tb = p.encode(), t.encode()
+    md = budget * (max(x, o + e) + 2) + 16
+    tab = (KmStep * (md + 1))(); w = C.c_uint64()
+    dend = oracle.L.km_build_steps(x, o, e, budget, md, tab, C.byref(w))
+    fin, dist, nops, cells = C.c_int(), C.c_int(), C.c_int(), C.c_long()
+    cap = 2 * dend + 16
+    ops = (C.c_uint8 * cap)()
+    assert oracle.L.km_align_pair(pb, len(pb), tb, len(tb), x, o, e, tab, dend, budget, 1, C.byref(fin),
+                                  C.byref(dist), ops, cap, C.byref(nops), C.byref(cells)) == 0
+    return fin.value, dist.value, list(ops[: nops.value])
+
+
+@pytest.mark.parametrize("pen", [(2, 3, 1), (5, 3, 2)])
+def test_ops_to_cigar_equals_oracle_decoder(lib, oracle, pen):
+    a = wfagpu.Aligner()
+    a.add_synthetic(0xB2000001, 150, 150, 0.05)
+    a.add_synthetic(0xB2000002, 8, 1000, 0.10)
+    a.add_sequences("ACGT", "ACGT")
+    for i in range(a.num_pairs):
+        p, t = a.pair(i)
+        fin, dist, ops = _model_ops(oracle, p, t, pen, 1000)
+        assert fin
+        n = len(ops)
+        words = (C.c_uint32 * ((n + 15) // 16 + 1))()
+        for j, op in enumerate(ops):
+            words[j >> 4] |= op << (2 * (j & 15))
+        cg = wfagpu.Cigar()
+        assert lib.wfagpu_ops_to_cigar(p.encode(), len(p), t.encode(), len(t), dist, words, n, C.byref(cg))
+        text = C.string_at(cg.buffer).decode() if cg.buffer else ""
+        assert text == oracle.align(p, t, *pen, 1000)["cigar"]
+
+
+def test_synthetic_generator_is_deterministic_and_has_the_asked_shape():
+    a, b = wfagpu.Aligner(), wfagpu.Aligner()
+    a.add_synthetic(42, 50, 1000, 0.10)
+    b.add_synthetic(42, 20, 1000, 0.10)
+    for i in range(20):
+        assert a.pair(i) == b.pair(i)
+    for i in range(50):
+        p, t = a.pair(i)
+        assert len(t) == 1000 and abs(len(p) - 1000) <= 100 and set(p + t) <= set("ACGT")
+    assert a.pair(0) != a.pair(1)
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    # on a machine without a CUDA device the library must fail loudly, never compute on the CPU
+    n = C.c_int(0)
+    lib.get_num_cuda_devices(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present")
+    a = wfagpu.Aligner()
+    a.add_sequences("ACGT", "ACGA")
+    assert a.initialize_parameters(2, 3, 1)
+    with pytest.raises(RuntimeError):
+        a.align()

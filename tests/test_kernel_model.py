@@ -1,0 +1,30 @@
+"""The CPU model of the B200 kernel's data flow (oracle/kernel_model.c: penalty-only step
+table, clean rings with NULL guards, decision bit-planes + traceback) must give exactly
+what the faithful restatement gives.  CPU only."""
+import pytest
+
+from test_oracle_ref import make_pairs, PENS
+
+
+@pytest.mark.parametrize("pen", PENS + [(1, 0, 1), (3, 5, 2), (7, 11, 3)])
+def test_model_equals_oracle(oracle, pen):
+    pairs = make_pairs(3, [(150, 0.05, 80), (700, 0.1, 10), (25, 0.35, 120), (0, 0, 1)])
+    pairs += [("", "ACGT"), ("ACGT", ""), ("ACGT", "ACGT"), ("A", "C"), ("ACGTACGTAC", "TTTTTTTTTT")]
+    for p, t in pairs:
+        r = oracle.align(p, t, *pen, 1200)
+        m = oracle.model_align(p, t, *pen, 1200)
+        assert r["finished"]
+        assert (m["finished"], m["distance"], m["cigar"]) == (r["finished"], r["distance"], r["cigar"])
+
+
+@pytest.mark.parametrize("pen", [(2, 3, 1), (4, 6, 2), (5, 3, 2)])
+def test_model_budget_rule_equals_oracle(oracle, pen):
+    # which pairs are over budget must match the reference rule (steps < max_steps - 1)
+    pairs = make_pairs(5, [(300, 0.1, 60)])
+    for budget in (12, 20, 31):
+        for p, t in pairs:
+            r = oracle.align(p, t, *pen, budget, cigar=False)
+            m = oracle.model_align(p, t, *pen, budget, cigar=False)
+            assert m["finished"] == r["finished"]
+            if r["finished"]:
+                assert m["distance"] == r["distance"]

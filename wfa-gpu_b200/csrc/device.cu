@@ -113,6 +113,10 @@ struct Slot {
     PinBuf<uint32_t> h_pool;
     PinBuf<uint32_t> h_counters;
     PinBuf<unsigned long long> h_cells;
+    PinBuf<wfagpu_step_t> h_steps;
+    int tab_key[4] = {-1, -1, -1, -1};
+    int tab_d_end = 0;
+    uint64_t tab_arena_units = 0;
     size_t n = 0;
     size_t ascii_bytes = 0;
     size_t packed_words = 0;
@@ -197,7 +201,7 @@ extern "C" void wfagpu_device_close_all(void)
             s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release();
             s.scratch.release(); s.steps.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
-            s.h_counters.release(); s.h_cells.release();
+            s.h_counters.release(); s.h_cells.release(); s.h_steps.release();
             for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
@@ -256,14 +260,7 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
     CK(cudaMemsetAsync(s.ascii.p + ascii_bytes, 0, 64, s.stream));
     CK(cudaMemcpyAsync(s.pairs.p, s.h_pairs.p, n * sizeof(wfagpu_pair_t), cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.order.p, s.h_order.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
-    CK(cudaMemsetAsync(s.counters.p, 0, CTR_WORDS * sizeof(uint32_t), s.stream));
-    CK(cudaMemsetAsync(s.cells.p, 0, sizeof(unsigned long long), s.stream));
     CK(cudaEventRecord(s.ev[1], s.stream));
-    PackParams pp{s.ascii.p, s.packed.p, s.pairs.p, (uint32_t)n};
-    launch_pack(pp, s.stream);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(s.ev[2], s.stream));
-    s.stats.launches += 1;
     s.stats.h2d_bytes += ascii_bytes + n * (sizeof(wfagpu_pair_t) + sizeof(uint32_t));
     s.have_events = true;
     return 0;
@@ -358,29 +355,35 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint
 
 /* Launch one pass over `n_items` entries of `order_dev`. */
 static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int max_steps, const uint32_t *order_dev,
-                       size_t n_items, uint32_t *retry_dev, bool ascii, int *n_cap_out, int *d_end_out)
+                       size_t n_items, uint32_t *retry_dev, bool ascii, bool first_pass, int *n_cap_out, int *d_end_out)
 {
     LaunchCfg c{};
     int rc = choose_cfg(d, plan.x, plan.o, plan.e, max_steps, s.max_len, n_items, ascii, &c);
     if (rc) return rc;
     /* step table */
     const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);
-    std::vector<wfagpu_step_t> tab((size_t)max_dist + 1);
-    uint64_t arena_units = 0;
-    const int d_end = wfagpu_build_step_table(plan.x, plan.o, plan.e, std::min(max_steps, c.n_cap + 2), max_dist,
-                                              tab.data(), &arena_units);
-    if (s.steps.ensure((size_t)d_end + 1)) return -1;
-    CK(cudaMemcpyAsync(s.steps.p, tab.data(), (size_t)d_end * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
-    CK(cudaStreamSynchronize(s.stream)); /* tab is a host temporary */
+    const int tab_steps = std::min(max_steps, c.n_cap + 2);
+    uint64_t arena_units = s.tab_arena_units;
+    int d_end = s.tab_d_end;
+    if (!(s.tab_key[0] == plan.x && s.tab_key[1] == plan.o && s.tab_key[2] == plan.e && s.tab_key[3] == tab_steps)) {
+        if (s.h_steps.ensure((size_t)max_dist + 1)) return -1;
+        CK(cudaStreamSynchronize(s.stream));  /* a previous pass may still be reading the pinned table */
+        d_end = wfagpu_build_step_table(plan.x, plan.o, plan.e, tab_steps, max_dist, s.h_steps.p, &arena_units);
+        if (d_end < 1) return -1;
+        if (s.steps.ensure((size_t)d_end + 1)) return -1;
+        CK(cudaMemcpyAsync(s.steps.p, s.h_steps.p, (size_t)d_end * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
+        s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = tab_steps;
+        s.tab_d_end = d_end;
+        s.tab_arena_units = arena_units;
+    }
 
     const size_t groups = (size_t)c.ctas * c.groups_per_cta;
     if (!plan.with_cigar) arena_units = 0;
     const uint32_t scratch_words = plan.with_cigar ? (uint32_t)((2 * (size_t)d_end + 31) / 16 + 2) : 1;
     if (s.arena.ensure(groups * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
     /* op pool: worst case for this pass on top of what is already used */
-    uint32_t pool_used = 0;
-    CK(cudaMemcpyAsync(&pool_used, s.counters.p + CTR_POOL, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
+    /* later passes run after read_counters(): the host copy of the pool head is current */
+    const uint32_t pool_used = first_pass ? 0u : s.h_counters.p[CTR_POOL];
     const size_t pool_need = (size_t)pool_used + (plan.with_cigar ? n_items * (size_t)scratch_words : 0) + 16;
     if (pool_need >= (1ull << 32)) {
         fprintf(stderr, "[wfagpu] op pool exceeds 32-bit offsets; use a smaller batch_size\n");
@@ -449,9 +452,20 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
         fprintf(stderr, "[wfagpu] banded kernels are not built yet\n");
         return -3;
     }
+    /* the batch may be re-aligned while it stays resident: start from clean counters */
+    s.stats.launches = 0;
+    s.stats.redispatched = 0;
+    s.stats.ascii_pairs = 0;
+    CK(cudaMemsetAsync(s.counters.p, 0, CTR_WORDS * sizeof(uint32_t), s.stream));
+    CK(cudaMemsetAsync(s.cells.p, 0, sizeof(unsigned long long), s.stream));
+    CK(cudaEventRecord(s.ev[2], s.stream));
+    PackParams pp{s.ascii.p, s.packed.p, s.pairs.p, (uint32_t)n};
+    launch_pack(pp, s.stream);
+    CK(cudaGetLastError());
+    s.stats.launches += 1;
     CK(cudaEventRecord(s.ev[3], s.stream));
     int n_cap = 0, d_end = 0;
-    int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, &n_cap, &d_end);
+    int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, true, &n_cap, &d_end);
     if (rc) return rc;
     CK(cudaEventRecord(s.ev[4], s.stream));
     return 0;
@@ -490,7 +504,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
             }
             steps = next;
             int n_cap = 0, d_end = 0;
-            int rc = launch_pass(d, s, plan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, &n_cap, &d_end);
+            int rc = launch_pass(d, s, plan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, false, &n_cap, &d_end);
             if (rc) return rc;
             if (read_counters()) return -1;
             if (n_cap + 2 < steps && s.h_counters.p[CTR_RETRY] > 0) {
@@ -511,7 +525,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     if (n_ascii > 0) {
         s.stats.ascii_pairs = n_ascii;
         int n_cap = 0, d_end = 0;
-        rc = launch_pass(d, s, plan, plan.max_steps, s.ascii_list.p, n_ascii, s.retry[0].p, true, &n_cap, &d_end);
+        rc = launch_pass(d, s, plan, plan.max_steps, s.ascii_list.p, n_ascii, s.retry[0].p, true, false, &n_cap, &d_end);
         if (rc) return rc;
         if (read_counters()) return -1;
         rc = redispatch(true, plan.max_steps);
@@ -538,11 +552,38 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     if (d->count_cells) s.stats.cells = s.h_cells.p[0];
     if (s.have_events) {
         cudaEventElapsedTime(&s.stats.ms_h2d, s.ev[0], s.ev[1]);
-        cudaEventElapsedTime(&s.stats.ms_pack, s.ev[1], s.ev[2]);
+        cudaEventElapsedTime(&s.stats.ms_pack, s.ev[2], s.ev[3]);
         cudaEventElapsedTime(&s.stats.ms_align, s.ev[3], s.ev[5]);
         cudaEventElapsedTime(&s.stats.ms_total, s.ev[0], s.ev[5]);
     }
     return 0;
+}
+
+extern "C" int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, float *ms_align)
+{
+    if (!d || slot < 0 || slot > 1) return -1;
+    CK(cudaSetDevice(d->dev));
+    Slot &s = d->slots[slot];
+    CK(cudaStreamSynchronize(s.stream));
+    if (ms_pack) cudaEventElapsedTime(ms_pack, s.ev[2], s.ev[3]);
+    if (ms_align) cudaEventElapsedTime(ms_align, s.ev[3], s.ev[4]);
+    return 0;
+}
+
+extern "C" int wfagpu_host_register(void *ptr, size_t bytes)
+{
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fprintf(stderr, "[wfagpu] cudaHostRegister failed: %s\n", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int wfagpu_host_unregister(void *ptr)
+{
+    return cudaHostUnregister(ptr) == cudaSuccess ? 0 : -1;
 }
 
 extern "C" void wfagpu_device_last_stats(wfagpu_device_t *d, int slot, wfagpu_batch_stats_t *st)
@@ -557,6 +598,9 @@ extern "C" int wfagpu_device_pack_only(wfagpu_device_t *d, const char *ascii, si
     if (!d) return -1;
     if (wfagpu_device_upload(d, 0, ascii, ascii_bytes, pairs, n)) return -1;
     Slot &s = d->slots[0];
+    PackParams pp{s.ascii.p, s.packed.p, s.pairs.p, (uint32_t)n};
+    launch_pack(pp, s.stream);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s.stream));
     if (packed_words < s.packed_words) return -1;
     CK(cudaMemcpy(packed_out, s.packed.p, s.packed_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));

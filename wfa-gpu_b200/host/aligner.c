@@ -22,6 +22,33 @@
 
 extern bool wfagpu_last_launch_ok(void); /* driver.c */
 
+/* The aligner owns its result array.  The reference frees it with the *current*
+ * pair count (lib/aligner.c:231-235), which overruns when pairs were added after
+ * wfagpu_initialize_parameters; here the allocated count lives in a hidden
+ * 16-byte prefix in front of the array. */
+#define RES_PREFIX 16
+static wfa_alignment_result_t *owned_results_new(size_t n, size_t cigar_len)
+{
+    char *blk = (char *)calloc(1, RES_PREFIX + (n ? n : 1) * sizeof(wfa_alignment_result_t));
+    if (!blk) return NULL;
+    *(size_t *)blk = n;
+    wfa_alignment_result_t *r = (wfa_alignment_result_t *)(blk + RES_PREFIX);
+    for (size_t i = 0; i < n; ++i) {
+        r[i].cigar.buffer = (char *)calloc(cigar_len, 1);
+        if (!r[i].cigar.buffer) return NULL;
+        r[i].cigar.buffer_size = cigar_len;
+    }
+    return r;
+}
+static void owned_results_free(wfa_alignment_result_t *r)
+{
+    if (!r) return;
+    char *blk = (char *)r - RES_PREFIX;
+    const size_t n = *(size_t *)blk;
+    for (size_t i = 0; i < n; ++i) free(r[i].cigar.buffer);
+    free(blk);
+}
+
 bool wfagpu_initialize_aligner(wfagpu_aligner_t *aligner)
 {
     if (!aligner) { ERR("Invalid aligner."); return false; }
@@ -116,8 +143,9 @@ bool wfagpu_initialize_parameters(wfagpu_aligner_t *aligner, affine_penalties_t 
     }
     wfagpu_set_default_options(&aligner->alignment_options, aligner->sequences_metadata, penalties,
                                aligner->num_sequence_pairs);
-    if (aligner->results) destroy_wfa_results(aligner->results, aligner->num_sequence_pairs);
-    return initialize_wfa_results(&aligner->results, aligner->num_sequence_pairs, FIRST_CIGAR_LEN);
+    owned_results_free(aligner->results);
+    aligner->results = owned_results_new(aligner->num_sequence_pairs, FIRST_CIGAR_LEN);
+    return aligner->results != NULL;
 }
 
 bool wfagpu_set_batch_size(wfagpu_aligner_t *aligner, size_t batch_size)
@@ -141,7 +169,7 @@ void wfagpu_destroy_aligner(wfagpu_aligner_t *aligner)
     if (!aligner) return;
     free(aligner->sequences_buffer);
     free(aligner->sequences_metadata);
-    if (aligner->results) destroy_wfa_results(aligner->results, aligner->num_sequence_pairs);
+    owned_results_free(aligner->results);
     aligner->sequences_buffer = NULL;
     aligner->sequences_metadata = NULL;
     aligner->results = NULL;
@@ -160,4 +188,18 @@ bool wfagpu_align(wfagpu_aligner_t *aligner)
     }
     /* the reference always returns true here; a failed GPU launch is reported instead */
     return wfagpu_last_launch_ok();
+}
+
+/* Extension: forget the CIGAR text of a previous wfagpu_align so that the same
+ * aligner can be aligned again (the reference appends to the old text). */
+void wfagpu_reset_results(wfagpu_aligner_t *aligner)
+{
+    if (!aligner || !aligner->results) return;
+    const size_t n = *(size_t *)((char *)aligner->results - RES_PREFIX);
+    for (size_t i = 0; i < n; ++i) {
+        aligner->results[i].error = 0;
+        aligner->results[i].cigar.last_free_position = 0;
+        if (aligner->results[i].cigar.buffer && aligner->results[i].cigar.buffer_size)
+            aligner->results[i].cigar.buffer[0] = 0;
+    }
 }

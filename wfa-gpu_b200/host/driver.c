@@ -115,34 +115,27 @@ static void fail_job(job_t *j)
     pthread_mutex_unlock(&j->mu);
 }
 
-static int submit(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f)
+/* Device-side view of pairs [from, from+n) of a host buffer laid out like
+ * wfagpu_add_sequences / the readers do (increasing 4-byte aligned offsets). */
+int wfagpu_pairs_from_metadata(sequence_pair_t *meta, size_t from, size_t n, size_t buf_size,
+                               wfagpu_pair_t *pairs, size_t *base_out, size_t *bytes_out)
 {
-    const sequence_pair_t *m = j->meta + f->from;
+    if (!meta || !pairs || n == 0) return -1;
+    sequence_pair_t *m = meta + from;
     const size_t base = m[0].pattern_offset;
-    const size_t last = m[f->n - 1].text_offset + m[f->n - 1].text_len + 1;
-    if (last < base || last > j->buf_size) {
+    const size_t last = m[n - 1].text_offset + m[n - 1].text_len + 1;
+    if (last < base || last > buf_size) {
         fprintf(stderr, "[!] ERROR: Reading out of sequences buffer. Aborting.\n");
         return -1;
     }
     const size_t bytes = last - base;
     if (bytes >= ((size_t)1 << 32)) {
-        fprintf(stderr, "[!] ERROR: a batch of %zu pairs spans %zu bytes; lower the batch size (32-bit offsets).\n", f->n, bytes);
+        fprintf(stderr, "[!] ERROR: a batch of %zu pairs spans %zu bytes; lower the batch size (32-bit offsets).\n", n, bytes);
         return -1;
     }
-    if (f->pairs_cap < f->n) {
-        free(f->pairs);
-        f->pairs = (wfagpu_pair_t *)malloc(f->n * sizeof(wfagpu_pair_t));
-        f->pairs_cap = f->n;
-    }
-    if (f->out_cap < f->n) {
-        free(f->out);
-        f->out = (wfagpu_pair_out_t *)malloc(f->n * sizeof(wfagpu_pair_out_t));
-        f->out_cap = f->n;
-    }
-    if (!f->pairs || !f->out) return -1;
     size_t words = 0;
-    for (size_t i = 0; i < f->n; ++i) {
-        wfagpu_pair_t *p = &f->pairs[i];
+    for (size_t i = 0; i < n; ++i) {
+        wfagpu_pair_t *p = &pairs[i];
         if (m[i].pattern_offset < base || m[i].text_offset < base ||
             m[i].pattern_offset + m[i].pattern_len > last || m[i].text_offset + m[i].text_len > last) {
             fprintf(stderr, "[!] ERROR: sequence metadata is not laid out in increasing offsets.\n");
@@ -156,11 +149,31 @@ static int submit(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f)
         p->flags = 0;
         p->reserved = 0;
         /* the reference rewrites the packed offsets of every batch (lib/align.cu:103-115, 363-377) */
-        j->meta[f->from + i].pattern_offset_packed = words * 4;
+        m[i].pattern_offset_packed = words * 4;
         words += ((((size_t)p->plen + 7) >> 3) + 1 + 3) & ~(size_t)3;
-        j->meta[f->from + i].text_offset_packed = words * 4;
+        m[i].text_offset_packed = words * 4;
         words += ((((size_t)p->tlen + 7) >> 3) + 1 + 3) & ~(size_t)3;
     }
+    if (base_out) *base_out = base;
+    if (bytes_out) *bytes_out = bytes;
+    return 0;
+}
+
+static int submit(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f)
+{
+    if (f->pairs_cap < f->n) {
+        free(f->pairs);
+        f->pairs = (wfagpu_pair_t *)malloc(f->n * sizeof(wfagpu_pair_t));
+        f->pairs_cap = f->n;
+    }
+    if (f->out_cap < f->n) {
+        free(f->out);
+        f->out = (wfagpu_pair_out_t *)malloc(f->n * sizeof(wfagpu_pair_out_t));
+        f->out_cap = f->n;
+    }
+    if (!f->pairs || !f->out) return -1;
+    size_t base = 0, bytes = 0;
+    if (wfagpu_pairs_from_metadata(j->meta, f->from, f->n, j->buf_size, f->pairs, &base, &bytes)) return -1;
     wfagpu_plan_t plan;
     memset(&plan, 0, sizeof(plan));
     plan.x = j->opt.penalties.x;

@@ -57,6 +57,21 @@ class Step(C.Structure):
     _fields_ = [("row_off", C.c_uint32), ("n", C.c_uint16), ("kind", C.c_uint16)]
 
 
+class Plan(C.Structure):
+    _fields_ = [("x", C.c_int), ("o", C.c_int), ("e", C.c_int), ("max_steps", C.c_int), ("band", C.c_int),
+                ("band_width", C.c_int), ("with_cigar", C.c_int), ("threads_hint", C.c_int), ("workers_hint", C.c_int)]
+
+
+class PairOut(C.Structure):
+    _fields_ = [("distance", C.c_int32), ("status", C.c_uint32), ("ops_off", C.c_uint32), ("n_ops", C.c_uint32)]
+
+
+class BatchStats(C.Structure):
+    _fields_ = [("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_total", C.c_float), ("launches", C.c_uint32), ("redispatched", C.c_uint32),
+                ("ascii_pairs", C.c_uint32), ("cells", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
 class DevPair(C.Structure):
     _fields_ = [("p_ascii", C.c_uint32), ("t_ascii", C.c_uint32), ("p_word", C.c_uint32), ("t_word", C.c_uint32),
                 ("plen", C.c_uint32), ("tlen", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
@@ -71,7 +86,8 @@ EXPORTS = [
     "wfagpu_build_step_table", "wfagpu_device_open", "wfagpu_device_close_all", "wfagpu_device_upload",
     "wfagpu_device_align", "wfagpu_device_download", "wfagpu_device_last_stats", "wfagpu_device_sm_count",
     "wfagpu_device_pack_only", "wfagpu_ops_to_cigar", "wfagpu_set_devices", "wfagpu_last_run_stats",
-    "wfagpu_synth_add_pairs",
+    "wfagpu_synth_add_pairs", "wfagpu_device_wait", "wfagpu_host_register", "wfagpu_host_unregister",
+    "wfagpu_pairs_from_metadata", "wfagpu_reset_results",
 ]
 
 _lib = None
@@ -101,6 +117,8 @@ def load():
     L.wfagpu_destroy_aligner.argtypes = [P(AlignerStruct)]
     L.wfagpu_destroy_aligner.restype = None
     L.wfagpu_set_devices.argtypes = [C.c_char_p]
+    L.wfagpu_reset_results.argtypes = [P(AlignerStruct)]
+    L.wfagpu_reset_results.restype = None
     L.wfagpu_last_run_stats.argtypes = [P(RunStats)]
     L.wfagpu_synth_add_pairs.argtypes = [P(AlignerStruct), C.c_uint64, C.c_size_t, C.c_int, C.c_double, C.c_double]
     L.wfagpu_synth_add_pairs.restype = C.c_bool
@@ -120,6 +138,17 @@ def load():
     L.wfagpu_device_open.restype = C.c_void_p
     L.wfagpu_device_pack_only.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, P(DevPair), C.c_size_t,
                                           P(C.c_uint32), C.c_size_t]
+    L.wfagpu_device_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, P(DevPair), C.c_size_t]
+    L.wfagpu_device_align.argtypes = [C.c_void_p, C.c_int, C.c_size_t, P(Plan), C.c_int]
+    L.wfagpu_device_wait.argtypes = [C.c_void_p, C.c_int, P(C.c_float), P(C.c_float)]
+    L.wfagpu_device_download.argtypes = [C.c_void_p, C.c_int, C.c_size_t, P(PairOut), P(P(C.c_uint32)),
+                                         P(C.c_size_t), P(C.c_uint32)]
+    L.wfagpu_device_last_stats.argtypes = [C.c_void_p, C.c_int, P(BatchStats)]
+    L.wfagpu_device_sm_count.argtypes = [C.c_void_p]
+    L.wfagpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.wfagpu_host_unregister.argtypes = [C.c_void_p]
+    L.wfagpu_pairs_from_metadata.argtypes = [P(SequencePair), C.c_size_t, C.c_size_t, C.c_size_t, P(DevPair),
+                                             P(C.c_size_t), P(C.c_size_t)]
     _lib = L
     return L
 
@@ -200,6 +229,16 @@ class Aligner:
         if not ok:
             raise RuntimeError("wfagpu_synth_add_pairs failed")
 
+    def reset_results(self):
+        self.L.wfagpu_reset_results(C.byref(self.s))
+
+    def pin_host_buffers(self):
+        """Page-lock the sequence buffer so H2D copies are asynchronous DMA."""
+        return self.L.wfagpu_host_register(self.s.sequences_buffer, self.s.sequences_buffer_len) == 0
+
+    def unpin_host_buffers(self):
+        self.L.wfagpu_host_unregister(self.s.sequences_buffer)
+
     def run_stats(self):
         st = RunStats()
         self.L.wfagpu_last_run_stats(C.byref(st))
@@ -208,3 +247,64 @@ class Aligner:
 
 def set_devices(spec):
     load().wfagpu_set_devices(_b(spec) if spec is not None else None)
+
+
+class ResidentBatch:
+    """A batch kept resident in HBM on one device: upload once, re-run the hot path
+    (pack + align + traceback kernels) any number of times.  Used by bench.py for the
+    device-resident throughput and by the tests to reach the C-ABI device layer."""
+
+    def __init__(self, aligner, device=0, slot=0):
+        self.L = load()
+        self.a = aligner
+        self.slot = slot
+        self.dev = self.L.wfagpu_device_open(device)
+        if not self.dev:
+            raise RuntimeError("no usable CUDA device (and no CPU fallback)")
+        n = aligner.num_pairs
+        self.n = n
+        self.pairs = (DevPair * n)()
+        base, nbytes = C.c_size_t(), C.c_size_t()
+        if self.L.wfagpu_pairs_from_metadata(aligner.s.sequences_metadata, 0, n, aligner.s.sequences_buffer_len,
+                                             self.pairs, C.byref(base), C.byref(nbytes)):
+            raise RuntimeError("bad sequence metadata")
+        self.base, self.nbytes = base.value, nbytes.value
+
+    def upload(self):
+        if self.L.wfagpu_device_upload(self.dev, self.slot, self.a.s.sequences_buffer + self.base, self.nbytes,
+                                       self.pairs, self.n):
+            raise RuntimeError("upload failed")
+
+    def plan(self, cigar=None):
+        o = self.a.options
+        return Plan(o.penalties.x, o.penalties.o, o.penalties.e, o.max_error, o.band, o.threads_per_block,
+                    int(o.compute_cigar if cigar is None else cigar), o.threads_per_block, o.num_workers)
+
+    def align(self, plan=None):
+        plan = plan or self.plan()
+        rc = self.L.wfagpu_device_align(self.dev, self.slot, self.n, C.byref(plan), 1)
+        if rc:
+            raise RuntimeError(f"wfagpu_device_align failed ({rc})")
+
+    def wait(self):
+        mp, ma = C.c_float(), C.c_float()
+        if self.L.wfagpu_device_wait(self.dev, self.slot, C.byref(mp), C.byref(ma)):
+            raise RuntimeError("device wait failed")
+        return mp.value, ma.value
+
+    def download(self):
+        out = (PairOut * self.n)()
+        ops = C.POINTER(C.c_uint32)()
+        used = C.c_size_t()
+        rc = self.L.wfagpu_device_download(self.dev, self.slot, self.n, out, C.byref(ops), C.byref(used), None)
+        if rc:
+            raise RuntimeError(f"wfagpu_device_download failed ({rc})")
+        return out, ops, used.value
+
+    def stats(self):
+        st = BatchStats()
+        self.L.wfagpu_device_last_stats(self.dev, self.slot, C.byref(st))
+        return {k: getattr(st, k) for k, _ in BatchStats._fields_}
+
+    def sm_count(self):
+        return self.L.wfagpu_device_sm_count(self.dev)
