@@ -269,7 +269,7 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
 /* Shared-memory / launch-shape policy (replaces available_shared_mem_per_block and
  * the <<<num_workers, tpb>>> choice of lib/sequence_alignment.cu:81-108,211-330). */
 static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint32_t max_len, size_t n_items,
-                      bool ascii, LaunchCfg *c)
+                      bool ascii, bool bt, LaunchCfg *c)
 {
     const int A = std::max(o + e, x) + 1, E1 = e + 1, G = A;
     const int rows = A + 2 * E1;
@@ -341,7 +341,7 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint
         c->group_threads = t;
     }
     const int threads = warp ? 32 * c->groups_per_cta : c->group_threads;
-    int occ = exact_max_ctas_per_sm(c->group_threads, c->groups_per_cta, c->smem, ascii);
+    int occ = exact_max_ctas_per_sm(c->group_threads, c->groups_per_cta, c->smem, ascii, bt);
     if (occ < 1) {
         fprintf(stderr, "[wfagpu] kernel configuration does not fit (threads=%d smem=%zu)\n", threads, c->smem);
         return -1;
@@ -358,7 +358,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
                        size_t n_items, uint32_t *retry_dev, bool ascii, bool first_pass, int *n_cap_out, int *d_end_out)
 {
     LaunchCfg c{};
-    int rc = choose_cfg(d, plan.x, plan.o, plan.e, max_steps, s.max_len, n_items, ascii, &c);
+    int rc = choose_cfg(d, plan.x, plan.o, plan.e, max_steps, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
     if (rc) return rc;
     /* step table */
     const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);

@@ -157,6 +157,27 @@ void launch_pack(const PackParams &p, cudaStream_t s)
 /* ======================================================================== */
 /*                            alignment kernel                              */
 /* ======================================================================== */
+/*
+ * All wavefront state lives in shared memory and is addressed through 32-bit
+ * shared-window addresses with explicit ld.shared / st.shared (one LDS.S16 per
+ * source offset, no generic-pointer arithmetic, no sign-extension fix-ups).
+ */
+__device__ __forceinline__ int lds_s16(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_16(uint32_t a, int v)
+{
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory");
+}
 
 template <bool WARP>
 struct Group {
@@ -171,28 +192,34 @@ struct Group {
 
 /* Bounded common prefix on packed words (replaces WF_extend_kernel,
  * lib/kernels/common_alignment_kernels.cuh:29-111): XOR + count-leading-zeros
- * on 32-bit windows; a window starts inside a single word thanks to the
- * 8-base stride layout, so the common case costs two shared loads. */
-__device__ __forceinline__ int extend_packed(const uint32_t *__restrict__ P, const uint32_t *__restrict__ T,
-                                             int plen, int tlen, int k, int off)
+ * on 32-bit windows.  With the 8-base stride layout a window of >= 9 bases
+ * starts inside one word, so the common case (a mismatch within 9 bases) costs
+ * two shared loads and no loop. */
+__device__ __forceinline__ int extend_packed(uint32_t Pa, uint32_t Ta, int plen, int tlen, int k, int off)
 {
-    int v = off - k, h = off;
+    const int v = off - k, h = off;
     const int rem = min(plen - v, tlen - h);
     if (rem < 0) return kOffNull;
-    int acc = 0;
-    while (true) {
-        const int vs = v & 7, hs = h & 7;
-        const uint32_t wp = P[v >> 3] << (2 * vs);
-        const uint32_t wt = T[h >> 3] << (2 * hs);
-        const int nvalid = 16 - max(vs, hs);
-        int eq = __clz((int)(wp ^ wt)) >> 1;
-        eq = min(eq, nvalid);
-        acc += eq;
-        if (eq < nvalid || acc >= rem) break;
-        v += eq;
-        h += eq;
+    const uint32_t uv = (uint32_t)v, uh = (uint32_t)h;
+    const uint32_t wp = lds_u32(Pa + ((uv >> 3) << 2)) << ((uv & 7u) * 2u);
+    const uint32_t wt = lds_u32(Ta + ((uh >> 3) << 2)) << ((uh & 7u) * 2u);
+    const int nvalid = 16 - (int)max(uv & 7u, uh & 7u);
+    int e1 = min(__clz((int)(wp ^ wt)) >> 1, rem);
+    if (e1 >= nvalid) {
+        /* long match (rare off the optimal path): keep going window by window */
+        int acc = nvalid;
+        while (acc < rem) {
+            const uint32_t v2 = uv + (uint32_t)acc, h2 = uh + (uint32_t)acc;
+            const uint32_t a = lds_u32(Pa + ((v2 >> 3) << 2)) << ((v2 & 7u) * 2u);
+            const uint32_t b = lds_u32(Ta + ((h2 >> 3) << 2)) << ((h2 & 7u) * 2u);
+            const int nv = 16 - (int)max(v2 & 7u, h2 & 7u);
+            const int eq = min(__clz((int)(a ^ b)) >> 1, nv);
+            acc += eq;
+            if (eq < nv) break;
+        }
+        e1 = min(acc, rem);
     }
-    return off + min(acc, rem);
+    return off + e1;
 }
 
 /* Byte-compare variant for pairs the packer flagged (non-ACGT bytes): plain
@@ -201,7 +228,7 @@ __device__ __forceinline__ int extend_packed(const uint32_t *__restrict__ P, con
 __device__ __forceinline__ int extend_ascii(const char *__restrict__ P, const char *__restrict__ T, int plen,
                                             int tlen, int k, int off)
 {
-    int v = off - k, h = off;
+    const int v = off - k, h = off;
     const int rem = min(plen - v, tlen - h);
     if (rem < 0) return kOffNull;
     int acc = 0;
@@ -209,22 +236,14 @@ __device__ __forceinline__ int extend_ascii(const char *__restrict__ P, const ch
     return off + acc;
 }
 
-template <bool ASCII>
-__device__ __forceinline__ int extend_any(const void *P, const void *T, int plen, int tlen, int k, int off)
-{
-    if (ASCII) return extend_ascii((const char *)P, (const char *)T, plen, tlen, k, off);
-    return extend_packed((const uint32_t *)P, (const uint32_t *)T, plen, tlen, k, off);
-}
-
 struct GroupCtl {
     uint64_t bar[2];     /* TMA completion barriers, one per sequence stage */
     uint32_t idx[2];     /* pair index staged in each buffer                */
-    uint32_t bytes_p[2]; /* unused by consumers; kept for debugging         */
     uint32_t n_ops;
     uint32_t ops_off;
 };
 
-template <bool WARP, bool ASCII>
+template <bool WARP, bool ASCII, bool BT>
 __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const __grid_constant__ KernelParams p)
 {
     using G = Group<WARP>;
@@ -233,38 +252,40 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
     const int tid = G::tid();
     const int gsz = G::size();
     const int lane = threadIdx.x & 31;
+    const int nwarps = WARP ? 1 : (int)(blockDim.x >> 5);
+    const int warp_in_group = WARP ? 0 : (int)(threadIdx.x >> 5);
     const int groups_per_cta = WARP ? (blockDim.x >> 5) : 1;
     const uint32_t group = blockIdx.x * groups_per_cta + G::id_in_cta();
 
-    /* ---- carve shared memory: [rings][seq stage 0][seq stage 1][ctl] per group ---- */
+    /* ---- carve shared memory: [rings][sequence stages][ctl] per group ---- */
     const int rows = p.A + 2 * p.E1;
-    const size_t ring_bytes = ((size_t)rows * p.row_stride * sizeof(int16_t) + 15) & ~(size_t)15;
-    const size_t seq_bytes = (size_t)p.seq_words * 4;          /* one sequence, one stage */
-    const size_t group_bytes = ring_bytes + (ASCII ? 0 : 2 * p.stages * seq_bytes) + sizeof(GroupCtl);
-    unsigned char *gbase = smem_raw + (size_t)G::id_in_cta() * ((group_bytes + 15) & ~(size_t)15);
-    int16_t *ring = reinterpret_cast<int16_t *>(gbase);
-    uint32_t *seqbuf = reinterpret_cast<uint32_t *>(gbase + ring_bytes);
-    GroupCtl *ctl = reinterpret_cast<GroupCtl *>(gbase + ring_bytes + (ASCII ? 0 : 2 * p.stages * seq_bytes));
+    const uint32_t row_bytes = (uint32_t)p.row_stride * 2u;
+    const uint32_t ring_bytes = ((uint32_t)rows * row_bytes + 15u) & ~15u;
+    const uint32_t seq_bytes = (uint32_t)p.seq_words * 4u;          /* one sequence, one stage */
+    const uint32_t seq_total = ASCII ? 0u : 2u * (uint32_t)p.stages * seq_bytes;
+    const uint32_t group_bytes = (ring_bytes + seq_total + (uint32_t)sizeof(GroupCtl) + 15u) & ~15u;
+    unsigned char *gbase = smem_raw + (size_t)G::id_in_cta() * group_bytes;
+    const uint32_t ring_sa = smem_u32(gbase);
+    const uint32_t seq_sa = ring_sa + ring_bytes;
+    GroupCtl *ctl = reinterpret_cast<GroupCtl *>(gbase + ring_bytes + seq_total);
 
-    int16_t *const Mring = ring + p.center;
-    int16_t *const Iring = Mring + (size_t)p.A * p.row_stride;
-    int16_t *const Dring = Iring + (size_t)p.E1 * p.row_stride;
+    const int x = p.x, e = p.e, A = p.A, E1 = p.E1, GW = p.G;
+    const int oe = p.o + p.e;
+    const uint32_t M0 = ring_sa + 2u * (uint32_t)p.center;          /* row 0 of M, diagonal 0 */
+    const uint32_t I0 = M0 + (uint32_t)A * row_bytes;
+    const uint32_t D0 = I0 + (uint32_t)E1 * row_bytes;
 
     uint4 *const arena = p.arena + (size_t)group * p.arena_units;
     uint32_t *const scratch = p.ops_scratch + (size_t)group * p.ops_scratch_words;
 
-    const int x = p.x, o = p.o, e = p.e, A = p.A, E1 = p.E1, GW = p.G;
-    const int oe = o + e;
-
-    /* ---- stage-0 prologue: pop the first pair and start its TMA load ---- */
     auto issue_load = [&](int stage, uint32_t idx) {
-        /* leader only */
+        /* leader only: both packed sequences of pair idx -> stage buffers, via TMA */
         if (ASCII) return;
         const wfagpu_pair_t pr = p.pairs[idx];
         const uint32_t pw = ((((pr.plen + 7u) >> 3) + 1u) + 3u) & ~3u;
         const uint32_t tw = ((((pr.tlen + 7u) >> 3) + 1u) + 3u) & ~3u;
-        uint32_t *dp = seqbuf + (size_t)(2 * stage) * p.seq_words;
-        uint32_t *dt = dp + p.seq_words;
+        unsigned char *dp = gbase + ring_bytes + (size_t)(2 * stage) * seq_bytes;
+        unsigned char *dt = dp + seq_bytes;
         fence_proxy_async();
         mbar_expect_tx(&ctl->bar[stage], (pw + tw) * 4u);
         tma_load_1d(dp, p.packed + pr.p_word, pw * 4u, &ctl->bar[stage]);
@@ -303,14 +324,14 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         const int plen = (int)pr.plen, tlen = (int)pr.tlen;
         const int kt = tlen - plen;
 
-        const void *Pseq, *Tseq;
-        if (ASCII) {
-            Pseq = p.ascii + pr.p_ascii;
-            Tseq = p.ascii + pr.t_ascii;
-        } else {
-            Pseq = seqbuf + (size_t)(2 * stage) * p.seq_words;
-            Tseq = seqbuf + (size_t)(2 * stage + 1) * p.seq_words;
-        }
+        const uint32_t Pa = seq_sa + (uint32_t)(2 * stage) * seq_bytes;
+        const uint32_t Ta = Pa + seq_bytes;
+        const char *const Pg = p.ascii + pr.p_ascii;
+        const char *const Tg = p.ascii + pr.t_ascii;
+        auto extend = [&](int k, int off) -> int {
+            if (ASCII) return extend_ascii(Pg, Tg, plen, tlen, k, off);
+            return extend_packed(Pa, Ta, plen, tlen, k, off);
+        };
 
         /* pairs flagged by the packer are left to the byte-compare launch */
         const bool skip = !ASCII && (pr.flags & WFAGPU_PAIR_HAS_N);
@@ -322,7 +343,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
             for (int i = tid; i < total; i += gsz) {
                 const int r = i / span;
                 const int k = i - r * span - 2 * GW;
-                ring[(size_t)r * p.row_stride + p.center + k] = (int16_t)kOffNull;
+                sts_16(M0 + (uint32_t)r * row_bytes + (uint32_t)(2 * k), kOffNull);
             }
         }
         if (!ASCII) mbar_wait(&ctl->bar[stage], (phase_bits >> stage) & 1u);
@@ -331,97 +352,105 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
 
         int dist = 0;
         bool finished = false;
-        unsigned long long my_cells = 0;
 
         if (!skip) {
-            if (tid == 0) Mring[0] = (int16_t)extend_any<ASCII>(Pseq, Tseq, plen, tlen, 0, 0);
+            if (tid == 0) sts_16(M0, extend(0, 0));
             G::sync();
-            if (kt == 0 && Mring[0] == tlen) {
+            if (kt == 0 && lds_s16(M0) == tlen) {
                 finished = true;
             } else {
                 wfagpu_step_t st_next = p.steps[1 < p.d_end ? 1 : 0];
+                /* Row addresses of the current score and of its sources are carried from
+                 * score to score (one add + wrap each) so that the diagonal loop sees them
+                 * as plain live values instead of re-deriving them. */
+                const uint32_t Mend = M0 + (uint32_t)A * row_bytes;
+                const uint32_t Iend = I0 + (uint32_t)E1 * row_bytes;
+                const uint32_t Dend = D0 + (uint32_t)E1 * row_bytes;
+                uint32_t aMc = M0, aIc = I0, aDc = D0;                      /* rows of score d (d = 0 now) */
+                uint32_t aMx = M0 + (uint32_t)((A - x % A) % A) * row_bytes;     /* row of score d - x     */
+                uint32_t aMo = M0 + (uint32_t)((A - oe % A) % A) * row_bytes;    /* row of score d - o - e */
+                uint32_t aIe = I0 + (uint32_t)((E1 - e % E1) % E1) * row_bytes;  /* row of score d - e     */
+                uint32_t aDe = D0 + (uint32_t)((E1 - e % E1) % E1) * row_bytes;
                 for (int d = 1; d < p.d_end; ++d) {
                     const wfagpu_step_t st = st_next;
                     if (d + 1 < p.d_end) st_next = p.steps[d + 1];
                     const int n = st.n;
                     if (n > p.n_cap) break;
-                    int16_t *const Mc = Mring + (size_t)(d % A) * p.row_stride;
-                    int16_t *const Ic = Iring + (size_t)(d % E1) * p.row_stride;
-                    int16_t *const Dc = Dring + (size_t)(d % E1) * p.row_stride;
+                    aMc += row_bytes; if (aMc == Mend) aMc = M0;
+                    aMx += row_bytes; if (aMx == Mend) aMx = M0;
+                    aMo += row_bytes; if (aMo == Mend) aMo = M0;
+                    aIc += row_bytes; if (aIc == Iend) aIc = I0;
+                    aIe += row_bytes; if (aIe == Iend) aIe = I0;
+                    aDc += row_bytes; if (aDc == Dend) aDc = D0;
+                    aDe += row_bytes; if (aDe == Dend) aDe = D0;
 
                     if (st.kind == WFAGPU_STEP_NULL) {
                         for (int k = -n - GW + tid; k <= n + GW; k += gsz) {
-                            Mc[k] = (int16_t)kOffNull;
-                            Ic[k] = (int16_t)kOffNull;
-                            Dc[k] = (int16_t)kOffNull;
+                            sts_16(aMc + (uint32_t)(2 * k), kOffNull);
+                            sts_16(aIc + (uint32_t)(2 * k), kOffNull);
+                            sts_16(aDc + (uint32_t)(2 * k), kOffNull);
                         }
                         G::sync();
                         continue;
                     }
                     if (st.kind == WFAGPU_STEP_M) {
-                        const int16_t *const Mx = Mring + (size_t)((d - x) % A) * p.row_stride;
                         for (int k = -n - GW + tid; k <= n + GW; k += gsz) {
-                            Ic[k] = (int16_t)kOffNull;
-                            Dc[k] = (int16_t)kOffNull;
+                            sts_16(aIc + (uint32_t)(2 * k), kOffNull);
+                            sts_16(aDc + (uint32_t)(2 * k), kOffNull);
                             int m = kOffNull;
                             if (k >= -n && k <= n) {
-                                m = (int)Mx[k] + 1;
-                                if (m >= 0) m = extend_any<ASCII>(Pseq, Tseq, plen, tlen, k, m);
-                                ++my_cells;
+                                m = lds_s16(aMx + (uint32_t)(2 * k)) + 1;
+                                if (m >= 0) m = extend(k, m);
                             }
-                            Mc[k] = (int16_t)m;
+                            sts_16(aMc + (uint32_t)(2 * k), m);
                         }
                     } else {
-                        const int16_t *const Mo = Mring + (size_t)(((d - oe) % A + A) % A) * p.row_stride;
-                        const int16_t *const Mx = Mring + (size_t)(((d - x) % A + A) % A) * p.row_stride;
-                        const int16_t *const Ie = Iring + (size_t)(((d - e) % E1 + E1) % E1) * p.row_stride;
-                        const int16_t *const De = Dring + (size_t)(((d - e) % E1 + E1) % E1) * p.row_stride;
-                        uint4 *const row = arena + st.row_off;
                         /* guard cells: NULL on both sides of [-n, n] */
                         for (int g = tid; g < 2 * GW; g += gsz) {
                             const int k = (g < GW) ? (-n - 1 - g) : (n + 1 + (g - GW));
-                            Mc[k] = (int16_t)kOffNull;
-                            Ic[k] = (int16_t)kOffNull;
-                            Dc[k] = (int16_t)kOffNull;
+                            sts_16(aMc + (uint32_t)(2 * k), kOffNull);
+                            sts_16(aIc + (uint32_t)(2 * k), kOffNull);
+                            sts_16(aDc + (uint32_t)(2 * k), kOffNull);
                         }
                         const int width = 2 * n + 1;
-                        for (int base = (tid & ~31); base < width; base += gsz) {
-                            const int idc = base + lane;
-                            const bool in = idc < width;
-                            uint32_t bI = 0, bD = 0, bM = 0;
-                            if (in) {
+                        uint4 *rp = arena + st.row_off + warp_in_group;
+                        /* one diagonal per lane, 32 consecutive diagonals per warp iteration */
+                        for (int idc = tid; (idc - lane) < width; idc += gsz, rp += nwarps) {
+                            bool bI = false, bD = false, bM0 = false, bM1 = false;
+                            if (idc < width) {
                                 const int k = idc - n;
-                                const int io = (int)Mo[k - 1] + 1;
-                                const int ie = (int)Ie[k - 1] + 1;
-                                const int pI = max(io * 2, ie * 2 + 1);
-                                const int I = pI >> 1;
-                                const int dopen = (int)Mo[k + 1];
-                                const int dext = (int)De[k + 1];
-                                const int pD = max(dopen * 2, dext * 2 + 1);
-                                const int D = pD >> 1;
-                                const int X = (int)Mx[k] + 1;
-                                const int pM = max(max(X * 4 + 2, D * 4 + 3), I * 4 + 1);
+                                const uint32_t kk = (uint32_t)(2 * k);
+                                const int io = lds_s16(aMo + kk - 2u) + 1;
+                                const int ie = lds_s16(aIe + kk - 2u) + 1;
+                                const int dopen = lds_s16(aMo + kk + 2u);
+                                const int dext = lds_s16(aDe + kk + 2u);
+                                const int X = lds_s16(aMx + kk) + 1;
+                                const int I = max(io, ie);
+                                const int D = max(dopen, dext);
+                                bI = ie >= io;                         /* extend beats open on ties */
+                                bD = dext >= dopen;
+                                /* D(3) beats X(2) beats I(1) on equal offsets */
+                                const int X4 = X * 4 + 2, I4 = I * 4 + 1;
+                                const int pM = max(max(X4, D * 4 + 3), I4);
                                 int M = pM >> 2;
-                                if (M >= 0) M = extend_any<ASCII>(Pseq, Tseq, plen, tlen, k, M);
-                                Ic[k] = (int16_t)I;
-                                Dc[k] = (int16_t)D;
-                                Mc[k] = (int16_t)M;
-                                bI = pI & 1;
-                                bD = pD & 1;
-                                bM = pM & 3;
-                                ++my_cells;
+                                if (M >= 0) M = extend(k, M);
+                                sts_16(aIc + kk, I);
+                                sts_16(aDc + kk, D);
+                                sts_16(aMc + kk, M);
+                                bM0 = pM != X4;                        /* winner is I(1) or D(3) */
+                                bM1 = pM != I4;                        /* winner is X(2) or D(3) */
                             }
-                            if (p.with_bt) {
+                            if (BT) {
                                 const uint32_t m0 = __ballot_sync(0xffffffffu, bI);
                                 const uint32_t m1 = __ballot_sync(0xffffffffu, bD);
-                                const uint32_t m2 = __ballot_sync(0xffffffffu, bM & 1u);
-                                const uint32_t m3 = __ballot_sync(0xffffffffu, bM & 2u);
-                                if (lane == 0) row[base >> 5] = make_uint4(m0, m1, m2, m3);
+                                const uint32_t m2 = __ballot_sync(0xffffffffu, bM0);
+                                const uint32_t m3 = __ballot_sync(0xffffffffu, bM1);
+                                if (lane == 0) *rp = make_uint4(m0, m1, m2, m3);
                             }
                         }
                     }
                     G::sync();
-                    if (kt >= -n && kt <= n && Mc[kt] == tlen) {
+                    if (kt >= -n && kt <= n && lds_s16(aMc + (uint32_t)(2 * kt)) == tlen) {
                         finished = true;
                         dist = d;
                         break;
@@ -433,10 +462,9 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         /* ---- traceback (leader): decision planes -> 2-bit ops, newest first ---- */
         if (tid == 0) {
             uint32_t n_ops = 0, ops_off = 0;
-            if (finished && p.with_bt && dist > 0) {
+            if (BT && finished && dist > 0) {
                 int cd = dist, ck = kt, comp = 0;
                 uint32_t word = 0;
-                __threadfence_block();
                 while (!(comp == 0 && cd == 0)) {
                     const wfagpu_step_t st = p.steps[cd];
                     uint32_t op;
@@ -499,13 +527,8 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
             }
             p.out[idx] = r;
         }
-        if (p.cells) {
-            /* optional work counter (profiling builds of the plan only) */
-            for (int s = 16; s > 0; s >>= 1) my_cells += __shfl_xor_sync(0xffffffffu, my_cells, s);
-            if (lane == 0 && my_cells) atomicAdd(p.cells, my_cells);
-        }
         G::sync();
-        {
+        if (BT) {
             /* copy the op words from the group's scratch into the pool (coalesced) */
             const uint32_t nw = (ctl->n_ops + 15u) >> 4;
             const uint32_t off = ctl->ops_off;
@@ -514,28 +537,41 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         G::sync();
         if (p.stages == 2) {
             stage ^= 1;
-        } else if (tid == 0) {
-            /* single buffer (shared memory is tight): fetch the next pair now */
-            const uint32_t nxt = pop();
-            ctl->idx[0] = nxt;
-            if (nxt != kInvalidIdx) issue_load(0, nxt);
+        } else {
+            if (tid == 0) {
+                /* single buffer (shared memory is tight): fetch the next pair now */
+                const uint32_t nxt = pop();
+                ctl->idx[0] = nxt;
+                if (nxt != kInvalidIdx) issue_load(0, nxt);
+            }
+            G::sync();
         }
-        if (p.stages != 2) G::sync();
     }
 }
 
-template <bool WARP, bool ASCII>
+/* ---- host-side launch helpers ---------------------------------------------- */
+
+template <bool WARP, bool ASCII, bool BT>
 static cudaError_t launch_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
-    auto kfn = wfa_exact_kernel<WARP, ASCII>;
+    auto kfn = wfa_exact_kernel<WARP, ASCII, BT>;
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, threads, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta,
-                        int stages)
+template <bool WARP, bool ASCII, bool BT>
+static int occupancy_one(int threads, size_t smem)
+{
+    auto kfn = wfa_exact_kernel<WARP, ASCII, BT>;
+    int n = 0;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
+    return n;
+}
+
+size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages)
 {
     const int rows = A + 2 * E1;
     const size_t ring_bytes = ((size_t)rows * row_stride * sizeof(int16_t) + 15) & ~(size_t)15;
@@ -544,44 +580,26 @@ size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups
     return group_bytes * (size_t)groups_per_cta;
 }
 
+#define WFAGPU_DISPATCH(FN, ...)                                                              \
+    (warp ? (ascii ? (bt ? FN<true, true, true>(__VA_ARGS__) : FN<true, true, false>(__VA_ARGS__))       \
+                   : (bt ? FN<true, false, true>(__VA_ARGS__) : FN<true, false, false>(__VA_ARGS__)))    \
+          : (ascii ? (bt ? FN<false, true, true>(__VA_ARGS__) : FN<false, true, false>(__VA_ARGS__))     \
+                   : (bt ? FN<false, false, true>(__VA_ARGS__) : FN<false, false, false>(__VA_ARGS__))))
+
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
-                         size_t smem_bytes, bool ascii_extend, cudaStream_t s)
+                         size_t smem_bytes, bool ascii, cudaStream_t s)
 {
     const bool warp = (group_threads == 32);
+    const bool bt = p.with_bt != 0;
     const int threads = warp ? 32 * groups_per_cta : group_threads;
-    if (warp) {
-        return ascii_extend ? launch_one<true, true>(p, threads, ctas, smem_bytes, s)
-                            : launch_one<true, false>(p, threads, ctas, smem_bytes, s);
-    }
-    return ascii_extend ? launch_one<false, true>(p, threads, ctas, smem_bytes, s)
-                        : launch_one<false, false>(p, threads, ctas, smem_bytes, s);
+    return WFAGPU_DISPATCH(launch_one, p, threads, ctas, smem_bytes, s);
 }
 
-int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend)
+int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii, bool bt)
 {
     const bool warp = (group_threads == 32);
     const int threads = warp ? 32 * groups_per_cta : group_threads;
-    int n = 0;
-    cudaError_t err;
-    if (warp) {
-        if (ascii_extend) {
-            cudaFuncSetAttribute(wfa_exact_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfa_exact_kernel<true, true>, threads, smem_bytes);
-        } else {
-            cudaFuncSetAttribute(wfa_exact_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfa_exact_kernel<true, false>, threads, smem_bytes);
-        }
-    } else {
-        if (ascii_extend) {
-            cudaFuncSetAttribute(wfa_exact_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfa_exact_kernel<false, true>, threads, smem_bytes);
-        } else {
-            cudaFuncSetAttribute(wfa_exact_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfa_exact_kernel<false, false>, threads, smem_bytes);
-        }
-    }
-    if (err != cudaSuccess) return 0;
-    return n;
+    return WFAGPU_DISPATCH(occupancy_one, threads, smem_bytes);
 }
 
 } // namespace wfagpu

@@ -76,6 +76,6 @@ void launch_pack(const PackParams &p, cudaStream_t s);
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
                          size_t smem_bytes, bool ascii_extend, cudaStream_t s);
 size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages);
-int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend);
+int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend, bool with_bt);
 
 } // namespace wfagpu
