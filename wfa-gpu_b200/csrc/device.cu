@@ -124,6 +124,7 @@ struct Slot {
     wfagpu_plan_t plan{};
     wfagpu_batch_stats_t stats{};
     bool have_events = false;
+    bool capped = false;      /* the first pass provisioned fewer diagonals than the budget allows */
 };
 
 } // namespace
@@ -134,6 +135,10 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
+    /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
+    int hint_dist = 0;
+    int hint_key[3] = {-1, -1, -1};
+    bool use_hint = true;
 };
 
 static std::mutex g_mu;
@@ -185,6 +190,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->force_stages = env_int("WFAGPU_STAGES", 0);
     d->force_ctas_per_sm = env_int("WFAGPU_CTAS_PER_SM", 0);
     d->force_warp = env_int("WFAGPU_WARP_KERNEL", -1);
+    d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
     g_devices.push_back(d);
     return d;
 }
@@ -267,8 +273,13 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
 }
 
 /* Shared-memory / launch-shape policy (replaces available_shared_mem_per_block and
- * the <<<num_workers, tpb>>> choice of lib/sequence_alignment.cu:81-108,211-330). */
-static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint32_t max_len, size_t n_items,
+ * the <<<num_workers, tpb>>> choice of lib/sequence_alignment.cu:81-108,211-330).
+ *
+ * The wavefront rings live in shared memory, so their width decides how many CTAs
+ * share an SM.  Measured on B200 (10 kbp / 5 %): 1 CTA x 1024 threads 62 k pairs/s,
+ * 2 x 512 95 k, 3 x 384 109 k -- more, smaller CTAs hide the per-score barrier.
+ * `n_want` is the half width the launch should be able to hold. */
+static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_t max_len, size_t n_items,
                       bool ascii, bool bt, LaunchCfg *c)
 {
     const int A = std::max(o + e, x) + 1, E1 = e + 1, G = A;
@@ -277,8 +288,7 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint
     const size_t smem_sm = d->prop.sharedMemPerMultiprocessor;     /* 228 KB */
     const int seq_words = (int)packed_words_for(max_len);
     c->A = A; c->E1 = E1; c->G = G; c->seq_words = seq_words;
-
-    int n_want = std::max(1, max_steps);                            /* n never exceeds the MDI step count */
+    n_want = std::max(1, n_want);
     auto rs = [&](int ncap) { return 2 * (ncap + 2 * G + 1) + 2; };
 
     bool warp = (rs(n_want) <= 400) && max_len <= 1024;
@@ -300,43 +310,38 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint
     }
     if (!warp) {
         c->groups_per_cta = 1;
-        /* try to fit two CTAs per SM; fall back to one CTA with as many diagonals as fit */
-        int stages = 2;
-        int n_cap = n_want;
-        size_t smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
-        const size_t half = (smem_sm - 2 * 1024) / 2;
-        if (smem > half) {
-            size_t s1 = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, 1);
-            if (s1 <= half) { stages = 1; smem = s1; }
-        }
-        if (smem > smem_max) {
-            stages = 1;
-            smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
-            if (smem > smem_max) {
-                /* clamp the half width to what one CTA can hold */
-                const size_t fixed = exact_smem_bytes(A, E1, 0, seq_words, 1, stages);
-                if (fixed + (size_t)rows * rs(1) * 2 > smem_max) return -2; /* sequences alone do not fit */
-                const size_t per_n = (size_t)rows * 2 * 2;          /* bytes per unit of n_cap */
-                n_cap = (int)((smem_max - fixed - 64) / per_n) - 2 * G - 2;
-                if (n_cap < 1) return -2;
-                smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
+        int best_k = 0, stages = 1, n_cap = n_want;
+        size_t smem = 0;
+        const int kmax = d->force_ctas_per_sm ? d->force_ctas_per_sm : 6;
+        for (int k = kmax; k >= 1 && !best_k; --k) {
+            /* every resident CTA also reserves 1 KB of system shared memory */
+            const size_t budget = std::min(smem_max, smem_sm / k - 1024);
+            for (int st = 2; st >= 1; --st) {
+                if (d->force_stages && st != d->force_stages) continue;
+                const size_t need = exact_smem_bytes(A, E1, rs(n_want), seq_words, 1, st);
+                if (need <= budget) { best_k = k; stages = st; smem = need; break; }
             }
         }
-        if (d->force_stages) {
-            stages = d->force_stages;
+        if (!best_k) {
+            /* does not fit even alone: hold as many diagonals as one CTA can */
+            stages = 1;
+            const size_t fixed = exact_smem_bytes(A, E1, 0, seq_words, 1, stages);
+            if (fixed + (size_t)rows * rs(1) * 2 > smem_max) return -2;   /* the sequences alone do not fit */
+            n_cap = (int)((smem_max - fixed - 64) / ((size_t)rows * 4)) - 2 * G - 2;
+            if (n_cap < 1) return -2;
             smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
-            if (smem > smem_max) return -2;
+            best_k = 1;
         }
         c->stages = stages;
         c->n_cap = n_cap;
         c->row_stride = rs(n_cap);
         c->center = n_cap + 2 * G + 1;
         c->smem = smem;
+        /* about 1152 threads per SM in total, never more threads than half the widest wavefront */
+        int t = best_k == 1 ? 1024 : (best_k == 2 ? 512 : ((1152 / best_k) / 32) * 32);
         const int width = 2 * n_cap + 1;
-        int t = 1024;
-        if (smem <= half) t = 512;            /* two CTAs per SM */
-        if (width <= 1024) t = std::min(t, 256);
-        if (width <= 384) t = std::min(t, 128);
+        while (t > 64 && t * 2 > width) t -= 32;
+        t = std::max(64, t);
         if (d->force_threads) t = d->force_threads;
         c->group_threads = t;
     }
@@ -353,29 +358,62 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int max_steps, uint
     return 0;
 }
 
+/* Remember the largest score of the batch whose results sit in s.h_out: the next first
+ * pass with the same penalties provisions its rings for that (plus a margin). */
+static void learn_hint(wfagpu_device *d, Slot &s, size_t n)
+{
+    int dmax = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (s.h_out.p[i].status & WFAGPU_ST_FINISHED) dmax = std::max(dmax, s.h_out.p[i].distance);
+    d->hint_dist = d->use_hint ? dmax : 0;
+    d->hint_key[0] = s.plan.x; d->hint_key[1] = s.plan.o; d->hint_key[2] = s.plan.e;
+}
+
 /* Launch one pass over `n_items` entries of `order_dev`. */
 static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int max_steps, const uint32_t *order_dev,
-                       size_t n_items, uint32_t *retry_dev, bool ascii, bool first_pass, int *n_cap_out, int *d_end_out)
+                       size_t n_items, uint32_t *retry_dev, bool ascii, bool first_pass, bool use_hint,
+                       bool *capped_out)
 {
-    LaunchCfg c{};
-    int rc = choose_cfg(d, plan.x, plan.o, plan.e, max_steps, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
-    if (rc) return rc;
-    /* step table */
+    /* step table for the full budget of this pass (cached per slot) */
     const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);
-    const int tab_steps = std::min(max_steps, c.n_cap + 2);
-    uint64_t arena_units = s.tab_arena_units;
-    int d_end = s.tab_d_end;
-    if (!(s.tab_key[0] == plan.x && s.tab_key[1] == plan.o && s.tab_key[2] == plan.e && s.tab_key[3] == tab_steps)) {
+    if (!(s.tab_key[0] == plan.x && s.tab_key[1] == plan.o && s.tab_key[2] == plan.e && s.tab_key[3] == max_steps)) {
         if (s.h_steps.ensure((size_t)max_dist + 1)) return -1;
         CK(cudaStreamSynchronize(s.stream));  /* a previous pass may still be reading the pinned table */
-        d_end = wfagpu_build_step_table(plan.x, plan.o, plan.e, tab_steps, max_dist, s.h_steps.p, &arena_units);
-        if (d_end < 1) return -1;
-        if (s.steps.ensure((size_t)d_end + 1)) return -1;
-        CK(cudaMemcpyAsync(s.steps.p, s.h_steps.p, (size_t)d_end * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
-        s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = tab_steps;
-        s.tab_d_end = d_end;
-        s.tab_arena_units = arena_units;
+        uint64_t units = 0;
+        const int de = wfagpu_build_step_table(plan.x, plan.o, plan.e, max_steps, max_dist, s.h_steps.p, &units);
+        if (de < 1) return -1;
+        if (s.steps.ensure((size_t)de + 1)) return -1;
+        CK(cudaMemcpyAsync(s.steps.p, s.h_steps.p, (size_t)de * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
+        s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = max_steps;
+        s.tab_d_end = de;
+        s.tab_arena_units = units;
     }
+    const wfagpu_step_t *tab = s.h_steps.p;
+    const int d_full = s.tab_d_end;
+    const int n_full = tab[d_full - 1].n;
+    /* half width to provision: the full budget, or (first pass only) what recent batches
+     * with these penalties needed plus a margin -- pairs that outgrow it are re-dispatched */
+    int n_want = n_full;
+    if (use_hint && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e) {
+        const long long dh = std::min<long long>((long long)d->hint_dist + d->hint_dist / 12 + 8, d_full - 1);
+        n_want = std::min(n_full, (int)tab[dh].n + 4);
+    }
+    LaunchCfg c{};
+    int rc = choose_cfg(d, plan.x, plan.o, plan.e, n_want, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
+    if (rc) return rc;
+    /* scores this launch can reach and the decision units they need */
+    int d_end = d_full;
+    uint64_t arena_units = s.tab_arena_units;
+    if (c.n_cap < n_full) {
+        int lo = 0, hi = d_full;                     /* first score whose half width exceeds n_cap */
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if ((int)tab[mid].n > c.n_cap) hi = mid; else lo = mid + 1;
+        }
+        d_end = lo;
+        arena_units = d_end < d_full ? tab[d_end].row_off : s.tab_arena_units;
+    }
+    *capped_out = c.n_cap < n_full;
 
     const size_t groups = (size_t)c.ctas * c.groups_per_cta;
     if (!plan.with_cigar) arena_units = 0;
@@ -434,8 +472,6 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         return -1;
     }
     s.stats.launches += 1;
-    *n_cap_out = c.n_cap;
-    *d_end_out = d_end;
     return 0;
 }
 
@@ -464,8 +500,7 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
     CK(cudaGetLastError());
     s.stats.launches += 1;
     CK(cudaEventRecord(s.ev[3], s.stream));
-    int n_cap = 0, d_end = 0;
-    int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, true, &n_cap, &d_end);
+    int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, true, true, &s.capped);
     if (rc) return rc;
     CK(cudaEventRecord(s.ev[4], s.stream));
     return 0;
@@ -490,45 +525,48 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     };
     if (read_counters()) return -1;
 
-    /* ---- re-dispatch tier: double the wavefront budget until everything finishes ---- */
-    auto redispatch = [&](bool ascii, int start_steps) -> int {
+    /* ---- re-dispatch tier: pairs that outgrew the provisioned rings first get the full
+     * budget, then the wavefront budget doubles until everything finishes ---- */
+    auto redispatch = [&](bool ascii, int start_steps, bool capped) -> int {
         int cur = 0;
         long long steps = start_steps;
         uint32_t pending = s.h_counters.p[CTR_RETRY];
         while (pending > 0) {
             s.stats.redispatched += pending;
-            const long long next = std::max<long long>(steps * 2, 64);
+            long long next = capped ? steps : std::max<long long>(steps * 2, 64);
             if (next > 30000) {
                 fprintf(stderr, "[wfagpu] %u pairs need more than %lld wavefront steps; not supported yet\n", pending, steps);
                 return -4;
             }
             steps = next;
-            int n_cap = 0, d_end = 0;
-            int rc = launch_pass(d, s, plan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, false, &n_cap, &d_end);
+            bool now_capped = false;
+            int rc = launch_pass(d, s, plan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, false, false,
+                                 &now_capped);
             if (rc) return rc;
             if (read_counters()) return -1;
-            if (n_cap + 2 < steps && s.h_counters.p[CTR_RETRY] > 0) {
-                fprintf(stderr, "[wfagpu] %u pairs exceed the on-chip wavefront capacity (n_cap=%d); not supported yet\n",
-                        s.h_counters.p[CTR_RETRY], n_cap);
+            if (now_capped && s.h_counters.p[CTR_RETRY] > 0) {
+                fprintf(stderr, "[wfagpu] %u pairs exceed the on-chip wavefront capacity; not supported yet\n",
+                        s.h_counters.p[CTR_RETRY]);
                 return -4;
             }
+            capped = false;
             pending = s.h_counters.p[CTR_RETRY];
             cur ^= 1;
         }
         return 0;
     };
-    int rc = redispatch(false, plan.max_steps);
+    int rc = redispatch(false, plan.max_steps, s.capped);
     if (rc) return rc;
 
     /* ---- pairs with non-ACGT bytes: byte-compare kernel on the ASCII copy ---- */
     const uint32_t n_ascii = s.h_counters.p[CTR_ASCII];
     if (n_ascii > 0) {
         s.stats.ascii_pairs = n_ascii;
-        int n_cap = 0, d_end = 0;
-        rc = launch_pass(d, s, plan, plan.max_steps, s.ascii_list.p, n_ascii, s.retry[0].p, true, false, &n_cap, &d_end);
+        bool capped = false;
+        rc = launch_pass(d, s, plan, plan.max_steps, s.ascii_list.p, n_ascii, s.retry[0].p, true, false, false, &capped);
         if (rc) return rc;
         if (read_counters()) return -1;
-        rc = redispatch(true, plan.max_steps);
+        rc = redispatch(true, plan.max_steps, capped);
         if (rc) return rc;
     }
     CK(cudaEventRecord(s.ev[5], s.stream));
@@ -544,6 +582,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     if (d->count_cells) CK(cudaMemcpyAsync(s.h_cells.p, s.cells.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
     memcpy(out, s.h_out.p, n * sizeof(wfagpu_pair_out_t));
+    learn_hint(d, s, n);
     if (pair_flags)
         for (size_t i = 0; i < n; ++i) pair_flags[i] = s.h_pairs.p[i].flags;
     if (ops) *ops = s.h_pool.p;
@@ -567,6 +606,14 @@ extern "C" int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, 
     CK(cudaStreamSynchronize(s.stream));
     if (ms_pack) cudaEventElapsedTime(ms_pack, s.ev[2], s.ev[3]);
     if (ms_align) cudaEventElapsedTime(ms_align, s.ev[3], s.ev[4]);
+    if (s.n && d->use_hint) {
+        /* read the result records back (16 B per pair) so that a re-run of the resident
+         * batch is provisioned like the next batch of a stream would be */
+        if (s.h_out.ensure(s.n)) return -1;
+        CK(cudaMemcpyAsync(s.h_out.p, s.out.p, s.n * sizeof(wfagpu_pair_out_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        learn_hint(d, s, s.n);
+    }
     return 0;
 }
 
