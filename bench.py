@@ -225,7 +225,8 @@ def run_ours(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            roofline["traffic"] = int(json.load(open(traffic_file))["dram_bytes_per_pair"] * PAIRS_PER_GPU)
+            roofline["traffic_note"] = "ncu dram bytes per pair (profiles/traffic.json) x pairs per launch"
         except Exception:
             pass
     roofline_int = {"bound": "issue", "cells_per_launch": cells, "nominal_instr_per_cell": 64,

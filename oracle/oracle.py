@@ -25,6 +25,8 @@ def build(ref=True):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
         if os.path.exists("/usr/local/cuda/bin/nvcc"):
             subprocess.check_call(["make", "-s", "-C", HERE, "refgpu"])
+        if os.path.exists(os.path.join(HERE, "..", "wfa-gpu_b200", "lib", "libwfagpu.so")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "dropin"])
 
 
 def _b(s):
