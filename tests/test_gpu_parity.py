@@ -74,3 +74,41 @@ def test_edge_cases(oracle):
         r = oracle.align(p, t, 2, 3, 1, 200)
         assert r["finished"]
         assert (a.error(i), a.cigar(i)) == (r["distance"], r["cigar"]), (p, t)
+
+
+def run_banded(specs, pen, cigar, band, window, max_error, seed=0xB2000000):
+    a = synth_aligner(specs, seed)
+    assert a.initialize_parameters(*pen)
+    a.options.compute_cigar = cigar
+    a.options.max_error = max_error
+    a.options.band = band
+    a.options.threads_per_block = window
+    a.align()
+    return a
+
+
+@pytest.mark.parametrize("cigar", [False, True])
+@pytest.mark.parametrize("specs,pen,band,window,max_error", [
+    ([(24, 10000, 0.01, 0.05)], (2, 3, 1), 25, 512, 3000),      # config 4: -B auto -t 512
+    ([(300, 1000, 0.10, 0.10)], (2, 3, 1), 25, 128, 800),       # narrow band: recall < 100 %
+    ([(300, 1000, 0.10, 0.10)], (2, 3, 1), 10, 64, 800),
+    ([(200, 700, 0.08, 0.08)], (5, 3, 2), 25, 96, 1200),
+    ([(200, 700, 0.08, 0.08)], (4, 6, 2), 50, 128, 1500),       # gcd > 1: null steps, stale ring slots
+])
+def test_banded_equals_oracle(oracle, cigar, specs, pen, band, window, max_error):
+    a = run_banded(specs, pen, cigar, band, window, max_error)
+    bad = []
+    n_subopt = 0
+    for i in range(a.num_pairs):
+        p, t = a.pair(i)
+        r = oracle.align(p, t, *pen, max_error, band=band, window=window, cigar=cigar)
+        assert r["finished"]
+        if a.error(i) != r["distance"] or (cigar and a.cigar(i) != r["cigar"]):
+            bad.append((i, a.error(i), r["distance"]))
+        if cigar:
+            # the heuristic may be sub-optimal, but the CIGAR must describe a real alignment of that score
+            assert oracle.cigar_score(p, t, a.cigar(i), *pen) == a.error(i)
+        exact = oracle.align(p, t, *pen, max_error, cigar=False)
+        n_subopt += exact["distance"] != a.error(i)
+    assert bad == []
+    assert n_subopt <= a.num_pairs // 2

@@ -42,3 +42,24 @@ def test_cigars_identical_to_reference_gpu(oracle, specs, pen, max_error):
     for i in range(0, len(pairs), step):
         r = oracle.align(*pairs[i], *pen, max_error)
         assert (r["distance"], r["cigar"]) == ref[i]
+
+
+@pytest.mark.parametrize("specs,pen,max_error,band,window", [
+    ([(48, 10000, 0.01, 0.05)], (2, 3, 1), 3000, 25, 512),     # config 4: -e 3000 -x -B auto -t 512
+    ([(400, 1000, 0.10, 0.10)], (2, 3, 1), 800, 25, 128),
+    ([(400, 1000, 0.10, 0.10)], (2, 3, 1), 800, 10, 64),
+])
+def test_banded_identical_to_reference_gpu(specs, pen, max_error, band, window):
+    if not refgpu.available():
+        pytest.skip("oracle/_ref/gpu/wfa.affine.gpu not built")
+    a = synth_aligner(specs, 0xB2002000)
+    assert a.initialize_parameters(*pen)
+    a.options.compute_cigar = True
+    a.options.max_error = max_error
+    a.options.band = band
+    a.options.threads_per_block = window
+    a.align()
+    pairs = [a.pair(i) for i in range(a.num_pairs)]
+    ref, wall, total = refgpu.run(pairs, pen, max_error, cigar=True, band=band, threads=window)
+    diff = [(i, a.error(i), ref[i][0]) for i in range(len(pairs)) if (a.error(i), a.cigar(i)) != ref[i]]
+    assert diff == []

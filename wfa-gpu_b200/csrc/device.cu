@@ -106,6 +106,7 @@ struct Slot {
     DevBuf<unsigned long long> cells;
     DevBuf<uint4> arena;
     DevBuf<uint32_t> scratch;
+    DevBuf<int32_t> band_lo;
     DevBuf<wfagpu_step_t> steps;
     PinBuf<wfagpu_pair_t> h_pairs;
     PinBuf<uint32_t> h_order;
@@ -205,7 +206,7 @@ extern "C" void wfagpu_device_close_all(void)
             s.ascii.release(); s.packed.release(); s.pairs.release(); s.order.release();
             s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
             s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release();
-            s.scratch.release(); s.steps.release();
+            s.scratch.release(); s.steps.release(); s.band_lo.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
             s.h_counters.release(); s.h_cells.release(); s.h_steps.release();
             for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -394,17 +395,45 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     /* half width to provision: the full budget, or (first pass only) what recent batches
      * with these penalties needed plus a margin -- pairs that outgrow it are re-dispatched */
     int n_want = n_full;
-    if (use_hint && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e) {
+    if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e) {
         const long long dh = std::min<long long>((long long)d->hint_dist + d->hint_dist / 12 + 8, d_full - 1);
         n_want = std::min(n_full, (int)tab[dh].n + 4);
     }
+    const bool banded = plan.band > 0;
     LaunchCfg c{};
-    int rc = choose_cfg(d, plan.x, plan.o, plan.e, n_want, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
+    int rc = 0;
+    int win = 0;
+    if (banded) {
+        /* adaptive band: window = the reference's threads_per_block (lib/sequence_alignment.cu:270-277) */
+        win = plan.band_width > 0 ? plan.band_width : 512;
+        c.A = std::max(plan.o + plan.e, plan.x) + 1; c.E1 = plan.e + 1; c.G = c.A;
+        c.seq_words = (int)packed_words_for(s.max_len);
+        c.groups_per_cta = 1;
+        c.group_threads = std::min(1024, std::max(32, (win + 31) & ~31));
+        c.stages = 2;
+        c.smem = banded_smem_bytes(c.A, win, c.seq_words, c.stages);
+        if (c.smem > d->prop.sharedMemPerBlockOptin) {
+            c.stages = 1;
+            c.smem = banded_smem_bytes(c.A, win, c.seq_words, c.stages);
+        }
+        if (c.smem > d->prop.sharedMemPerBlockOptin) {
+            fprintf(stderr, "[wfagpu] band of %d diagonals does not fit in shared memory\n", win);
+            return -2;
+        }
+        c.n_cap = n_full; c.row_stride = win; c.center = 0;
+        int occ = banded_max_ctas_per_sm(c.group_threads, c.smem, ascii, plan.with_cigar != 0);
+        if (occ < 1) return -1;
+        c.ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ * d->prop.multiProcessorCount, n_items));
+    } else {
+        rc = choose_cfg(d, plan.x, plan.o, plan.e, n_want, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
+    }
     if (rc) return rc;
     /* scores this launch can reach and the decision units they need */
     int d_end = d_full;
     uint64_t arena_units = s.tab_arena_units;
-    if (c.n_cap < n_full) {
+    if (banded) {
+        arena_units = (uint64_t)n_full * (uint64_t)((win + 31) >> 5);
+    } else if (c.n_cap < n_full) {
         int lo = 0, hi = d_full;                     /* first score whose half width exceeds n_cap */
         while (lo < hi) {
             const int mid = (lo + hi) / 2;
@@ -419,6 +448,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     if (!plan.with_cigar) arena_units = 0;
     const uint32_t scratch_words = plan.with_cigar ? (uint32_t)((2 * (size_t)d_end + 31) / 16 + 2) : 1;
     if (s.arena.ensure(groups * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
+    const uint32_t band_lo_words = (banded && plan.with_cigar) ? (uint32_t)d_end + 1 : 0;
+    if (s.band_lo.ensure(groups * (size_t)band_lo_words + 1)) return -1;
     /* op pool: worst case for this pass on top of what is already used */
     /* later passes run after read_counters(): the host copy of the pool head is current */
     const uint32_t pool_used = first_pass ? 0u : s.h_counters.p[CTR_POOL];
@@ -449,6 +480,10 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.seq_words = c.seq_words;
     kp.with_bt = plan.with_cigar;
     kp.stages = c.stages;
+    kp.band = plan.band;
+    kp.win = win;
+    kp.band_lo = s.band_lo.p;
+    kp.band_lo_words = band_lo_words;
     kp.arena = s.arena.p;
     kp.arena_units = arena_units;
     kp.ops_scratch = s.scratch.p;
@@ -466,7 +501,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d arena=%.1f MB\n",
                 n_items, max_steps, c.n_cap, d_end, c.group_threads, c.groups_per_cta, c.ctas, c.stages, c.smem,
                 (int)ascii, groups * arena_units * 16.0 / 1e6);
-    cudaError_t e = launch_exact(kp, c.group_threads, c.groups_per_cta, c.ctas, c.smem, ascii, s.stream);
+    cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
+                           : launch_exact(kp, c.group_threads, c.groups_per_cta, c.ctas, c.smem, ascii, s.stream);
     if (e != cudaSuccess) {
         fprintf(stderr, "[wfagpu] alignment kernel launch failed: %s\n", cudaGetErrorString(e));
         return -1;
@@ -484,10 +520,6 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
     if (n != s.n) return -1;
     s.plan = *plan;
     if (n == 0) return 0;
-    if (plan->band > 0) {
-        fprintf(stderr, "[wfagpu] banded kernels are not built yet\n");
-        return -3;
-    }
     /* the batch may be re-aligned while it stays resident: start from clean counters */
     s.stats.launches = 0;
     s.stats.redispatched = 0;

@@ -549,6 +549,391 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
     }
 }
 
+/* ======================================================================== */
+/*                         banded (adaptive band) kernel                    */
+/* ======================================================================== */
+/*
+ * Replaces alignment_kernel_aband / distance_kernel_aband
+ * (lib/kernels/sequence_alignment_kernel_aband.cu:145-391, 596-725;
+ *  lib/kernels/sequence_distance_kernel_aband.cu:99-147).
+ *
+ * The heuristic is not exact, so the reference's memory semantics are kept
+ * as they are: rings of depth A for M, I and D, every slot with its own [lo, hi]
+ * window (offsets stored at k - lo), slots are not cleared on null steps and
+ * reads outside a slot's window return NULL.  Window rule (aband.cu:167-205):
+ * grow by one on both sides, clip alternately hi--, lo++ to the band width,
+ * and every `band` scores -- once the mismatch source is full width --
+ * re-centre on the first diagonal with the smallest distance to the target.
+ * The serial O(W) scan every thread runs in the reference ("TODO: make
+ * cooperative") is a lexicographic (distance, diagonal) block reduction here.
+ */
+struct BandCtl {
+    uint64_t bar[2];
+    uint32_t idx[2];
+    uint32_t n_ops;
+    uint32_t ops_off;
+    int new_center;
+    int pad;
+    unsigned long long red[32];
+};
+
+__device__ __forceinline__ int band_get(uint32_t row, int lo, int hi, int k)
+{
+    return (k >= lo && k <= hi) ? lds_s16(row + (uint32_t)(2 * (k - lo))) : kOffNull;
+}
+
+template <bool ASCII, bool BT>
+__global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_constant__ KernelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, gsz = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = gsz >> 5;
+    const int x = p.x, e = p.e, A = p.A, W = p.win;
+    const int oe = p.o + p.e;
+    const uint32_t row_bytes = (uint32_t)((W + 7) & ~7) * 2u;
+    const uint32_t comp_bytes = (uint32_t)A * row_bytes;
+    const uint32_t ring_bytes = (3u * comp_bytes + 15u) & ~15u;
+    const uint32_t lohi_bytes = (uint32_t)(((3 * A * 2 * (int)sizeof(int)) + 15) & ~15);
+    const uint32_t seq_bytes = (uint32_t)p.seq_words * 4u;
+    const uint32_t seq_total = ASCII ? 0u : 2u * (uint32_t)p.stages * seq_bytes;
+    const uint32_t M0 = smem_u32(smem_raw);
+    const uint32_t I0 = M0 + comp_bytes, D0 = I0 + comp_bytes;
+    int *const LO = reinterpret_cast<int *>(smem_raw + ring_bytes);   /* [comp][slot] */
+    int *const HI = LO + 3 * A;
+    const uint32_t seq_sa = M0 + ring_bytes + lohi_bytes;
+    BandCtl *ctl = reinterpret_cast<BandCtl *>(smem_raw + ring_bytes + lohi_bytes + seq_total);
+
+    const uint32_t group = blockIdx.x;
+    const uint32_t row_units = (uint32_t)((W + 31) >> 5);
+    uint4 *const arena = p.arena + (size_t)group * p.arena_units;
+    int32_t *const lo_tab = p.band_lo + (size_t)group * p.band_lo_words;
+    uint32_t *const scratch = p.ops_scratch + (size_t)group * p.ops_scratch_words;
+
+    auto issue_load = [&](int stage, uint32_t idx) {
+        if (ASCII) return;
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const uint32_t pw = ((((pr.plen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        const uint32_t tw = ((((pr.tlen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        unsigned char *dp = smem_raw + ring_bytes + lohi_bytes + (size_t)(2 * stage) * seq_bytes;
+        unsigned char *dt = dp + seq_bytes;
+        fence_proxy_async();
+        mbar_expect_tx(&ctl->bar[stage], (pw + tw) * 4u);
+        tma_load_1d(dp, p.packed + pr.p_word, pw * 4u, &ctl->bar[stage]);
+        tma_load_1d(dt, p.packed + pr.t_word, tw * 4u, &ctl->bar[stage]);
+    };
+    auto pop = [&]() -> uint32_t {
+        const uint32_t pos = atomicAdd(p.queue, 1u);
+        return pos < p.n_items ? p.order[pos] : kInvalidIdx;
+    };
+    if (tid == 0) {
+        if (!ASCII) {
+            mbar_init(&ctl->bar[0], 1);
+            mbar_init(&ctl->bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        const uint32_t first = pop();
+        ctl->idx[0] = first;
+        if (first != kInvalidIdx) issue_load(0, first);
+    }
+    __syncthreads();
+
+    int stage = 0;
+    uint32_t phase_bits = 0;
+    while (true) {
+        const uint32_t idx = ctl->idx[stage];
+        if (idx == kInvalidIdx) break;
+        if (tid == 0 && p.stages == 2) {
+            const uint32_t nxt = pop();
+            ctl->idx[stage ^ 1] = nxt;
+            if (nxt != kInvalidIdx) issue_load(stage ^ 1, nxt);
+        }
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const int plen = (int)pr.plen, tlen = (int)pr.tlen;
+        const int kt = tlen - plen;
+        const int kt_abs = kt < 0 ? -kt : kt;
+        const uint32_t Pa = seq_sa + (uint32_t)(2 * stage) * seq_bytes;
+        const uint32_t Ta = Pa + seq_bytes;
+        const char *const Pg = p.ascii + pr.p_ascii;
+        const char *const Tg = p.ascii + pr.t_ascii;
+        auto extend = [&](int k, int off) -> int {
+            if (ASCII) return extend_ascii(Pg, Tg, plen, tlen, k, off);
+            return extend_packed(Pa, Ta, plen, tlen, k, off);
+        };
+        const bool skip = !ASCII && (pr.flags & WFAGPU_PAIR_HAS_N);
+
+        /* every slot starts as the one-diagonal window [0, 0] holding NULL (aband.cu:543-578) */
+        for (int i = tid; i < 3 * A; i += gsz) {
+            LO[i] = 0;
+            HI[i] = 0;
+            sts_16(M0 + (uint32_t)i * row_bytes, kOffNull);
+        }
+        if (!ASCII) mbar_wait(&ctl->bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        __syncthreads();
+
+        int dist = 0;
+        bool finished = false;
+        if (!skip) {
+            if (tid == 0) sts_16(M0, extend(0, 0));
+            __syncthreads();
+            if (kt == 0 && lds_s16(M0) == tlen) {
+                finished = true;
+            } else {
+                int sM = 0;                                  /* ring slot of the current score: d mod A */
+                for (int d = 1; d < p.d_end; ++d) {
+                    const wfagpu_step_t st = p.steps[d];
+                    sM = (sM + 1 == A) ? 0 : sM + 1;
+                    if (st.kind == WFAGPU_STEP_NULL) continue;
+                    int sx = sM - x;  if (sx < 0) sx += A;
+                    const uint32_t aMx = M0 + (uint32_t)sx * row_bytes;
+                    const int xlo = LO[sx], xhi = HI[sx];
+                    const uint32_t aMc = M0 + (uint32_t)sM * row_bytes;
+                    int lo, hi;
+                    if (st.kind == WFAGPU_STEP_M) {
+                        lo = xlo; hi = xhi;
+                        __syncthreads();                     /* everyone has read LO/HI before they change */
+                        for (int k = lo + tid; k <= hi; k += gsz) {
+                            int m = lds_s16(aMx + (uint32_t)(2 * (k - xlo))) + 1;
+                            if (m >= 0) m = extend(k, m);
+                            sts_16(aMc + (uint32_t)(2 * (k - lo)), m);
+                        }
+                        if (tid == 0) { LO[sM] = lo; HI[sM] = hi; }
+                    } else {
+                        int so = sM - oe; if (so < 0) so += A;
+                        int sg = sM - e;  if (sg < 0) sg += A;
+                        const uint32_t aMo = M0 + (uint32_t)so * row_bytes;
+                        const uint32_t aIe = I0 + (uint32_t)sg * row_bytes;
+                        const uint32_t aDe = D0 + (uint32_t)sg * row_bytes;
+                        const uint32_t aIc = I0 + (uint32_t)sM * row_bytes;
+                        const uint32_t aDc = D0 + (uint32_t)sM * row_bytes;
+                        const int olo = LO[so], ohi = HI[so];
+                        const int ilo = LO[A + sg], ihi = HI[A + sg];
+                        const int dlo = LO[2 * A + sg], dhi = HI[2 * A + sg];
+                        const int hi_ID = max(ohi, max(ihi, dhi)) + 1;
+                        const int lo_ID = min(olo, min(ilo, dlo)) - 1;
+                        hi = max(xhi, hi_ID);
+                        lo = min(xlo, lo_ID);
+                        const int excess = (hi - lo) - (W - 1);
+                        if (excess > 0) { hi -= (excess + 1) >> 1; lo += excess >> 1; }
+                        if ((xhi - xlo) >= W - 1 && (d % p.band) == 0) {
+                            /* first diagonal of [xlo, xhi) with the smallest distance to the target */
+                            unsigned long long best = ~0ull;
+                            for (int i = xlo + tid; i < xhi; i += gsz) {
+                                const int off = lds_s16(aMx + (uint32_t)(2 * (i - xlo)));
+                                const int left_v = (int)(short)(plen - (off - i));
+                                const int left_h = (int)(short)(tlen - off);
+                                const int dt = off >= 0 ? max(left_v, left_h) : 0x7fffffff;
+                                const unsigned long long key =
+                                    ((unsigned long long)((unsigned)dt ^ 0x80000000u) << 32) | (unsigned)(i - xlo);
+                                best = key < best ? key : best;
+                            }
+                            for (int s = 16; s > 0; s >>= 1) {
+                                const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
+                                best = o < best ? o : best;
+                            }
+                            if (lane == 0) ctl->red[warp] = best;
+                            __syncthreads();
+                            if (warp == 0) {
+                                unsigned long long b = lane < nwarps ? ctl->red[lane] : ~0ull;
+                                for (int s = 16; s > 0; s >>= 1) {
+                                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, b, s);
+                                    b = o < b ? o : b;
+                                }
+                                if (lane == 0) {
+                                    int c = xlo;
+                                    if (b != ~0ull) {
+                                        const int dt = (int)((unsigned)(b >> 32) ^ 0x80000000u);
+                                        if (dt < 2 * (tlen + plen)) c = xlo + (int)(unsigned)(b & 0xffffffffu);
+                                    }
+                                    ctl->new_center = c;
+                                }
+                            }
+                            __syncthreads();
+                            lo = ctl->new_center - (W / 2);
+                            hi = lo + W - 1;
+                        }
+                        __syncthreads();                     /* sources' LO/HI are read; the slot may change now */
+                        if (tid == 0) {
+                            LO[sM] = lo; HI[sM] = hi;
+                            LO[A + sM] = lo; HI[A + sM] = hi;
+                            LO[2 * A + sM] = lo; HI[2 * A + sM] = hi;
+                            if (BT) lo_tab[d] = lo;
+                        }
+                        uint4 *rp = arena + (size_t)((uint32_t)st.n - 1u) * row_units + warp;
+                        const int width = hi - lo + 1;
+                        for (int idc = tid; (idc - lane) < width; idc += gsz, rp += nwarps) {
+                            bool bI = false, bD = false, bM0 = false, bM1 = false;
+                            if (idc < width) {
+                                const int k = lo + idc;
+                                const int io = band_get(aMo, olo, ohi, k - 1) + 1;
+                                const int ie = band_get(aIe, ilo, ihi, k - 1) + 1;
+                                const int dopen = band_get(aMo, olo, ohi, k + 1);
+                                const int dext = band_get(aDe, dlo, dhi, k + 1);
+                                const int X = band_get(aMx, xlo, xhi, k) + 1;
+                                /* the reference keeps int16 values between the steps */
+                                const int I = (int)(short)max(io, ie);
+                                const int D = (int)(short)max(dopen, dext);
+                                bI = ie >= io;
+                                bD = dext >= dopen;
+                                const int X4 = (int)(short)X * 4 + 2, I4 = I * 4 + 1;
+                                const int pM = max(max(X4, D * 4 + 3), I4);
+                                int M = pM >> 2;
+                                if (M >= 0) M = extend(k, M);
+                                const uint32_t kk = (uint32_t)(2 * idc);
+                                sts_16(aIc + kk, I);
+                                sts_16(aDc + kk, D);
+                                sts_16(aMc + kk, M);
+                                bM0 = pM != X4;
+                                bM1 = pM != I4;
+                            }
+                            if (BT) {
+                                const uint32_t m0 = __ballot_sync(0xffffffffu, bI);
+                                const uint32_t m1 = __ballot_sync(0xffffffffu, bD);
+                                const uint32_t m2 = __ballot_sync(0xffffffffu, bM0);
+                                const uint32_t m3 = __ballot_sync(0xffffffffu, bM1);
+                                if (lane == 0) *rp = make_uint4(m0, m1, m2, m3);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (kt_abs <= d) {
+                        const int t = band_get(aMc, lo, hi, kt);
+                        if (t == tlen) { finished = true; dist = d; break; }
+                        if (t > tlen) break;                 /* aband.cu:678-681 */
+                    }
+                }
+            }
+        }
+
+        /* ---- traceback: like the exact kernel, plus the per-score window origin and the
+         * resolution of stale ring slots (a null score keeps the slot's previous owner) ---- */
+        if (tid == 0) {
+            uint32_t n_ops = 0, ops_off = 0;
+            if (BT && finished && dist > 0) {
+                int cd = dist, ck = kt, comp = 0;
+                uint32_t word = 0;
+                bool bad = false;
+                auto resolveM = [&](int dd) { while (dd > 0 && p.steps[dd].kind == WFAGPU_STEP_NULL) dd -= A; return dd; };
+                auto resolveG = [&](int dd) { while (dd > 0 && p.steps[dd].kind != WFAGPU_STEP_MDI) dd -= A; return dd; };
+                while (!(comp == 0 && cd == 0)) {
+                    if (cd < 0) { bad = true; break; }
+                    const wfagpu_step_t st = p.steps[cd];
+                    uint32_t op;
+                    if (comp == 0 && st.kind == WFAGPU_STEP_M) {
+                        op = OP_SUB;
+                        cd = resolveM(cd - x);
+                    } else {
+                        if (st.kind != WFAGPU_STEP_MDI) { bad = true; break; }
+                        const int ii = ck - lo_tab[cd];
+                        if (ii < 0 || ii >= W) { bad = true; break; }
+                        const uint4 dec = arena[(size_t)((uint32_t)st.n - 1u) * row_units + (ii >> 5)];
+                        const int b = ii & 31;
+                        if (comp == 0) {
+                            op = OP_SUB;
+                            const int mop = (int)((dec.z >> b) & 1u) | (int)(((dec.w >> b) & 1u) << 1);
+                            if (mop == OP_SUB) cd = resolveM(cd - x);
+                            else if (mop == OP_INS) comp = 1;
+                            else comp = 2;
+                        } else if (comp == 1) {
+                            op = OP_INS;
+                            ck -= 1;
+                            if ((dec.x >> b) & 1u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+                        } else {
+                            op = OP_DEL;
+                            ck += 1;
+                            if ((dec.y >> b) & 1u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+                        }
+                    }
+                    word |= op << (2 * (n_ops & 15u));
+                    ++n_ops;
+                    if ((n_ops & 15u) == 0) { scratch[(n_ops >> 4) - 1] = word; word = 0; }
+                    if ((n_ops >> 4) >= p.ops_scratch_words) { bad = true; break; }
+                }
+                if (bad) { n_ops = 0; finished = false; }
+                if (n_ops & 15u) scratch[n_ops >> 4] = word;
+                const uint32_t nw = (n_ops + 15u) >> 4;
+                ops_off = atomicAdd(p.ops_pool_head, nw);
+                if (ops_off + nw > p.ops_pool_words) { n_ops = 0; finished = false; }
+            }
+            ctl->n_ops = n_ops;
+            ctl->ops_off = ops_off;
+            wfagpu_pair_out_t r;
+            r.distance = finished ? dist : 0;
+            r.ops_off = ops_off;
+            r.n_ops = n_ops;
+            if (skip) {
+                r.status = WFAGPU_ST_NEEDS_ASCII;
+                p.ascii_list[atomicAdd(p.ascii_count, 1u)] = idx;
+            } else if (finished) {
+                r.status = WFAGPU_ST_FINISHED;
+            } else {
+                r.status = WFAGPU_ST_OVERBUDGET;
+                p.retry_list[atomicAdd(p.retry_count, 1u)] = idx;
+            }
+            p.out[idx] = r;
+        }
+        __syncthreads();
+        if (BT) {
+            const uint32_t nw = (ctl->n_ops + 15u) >> 4;
+            const uint32_t off = ctl->ops_off;
+            for (uint32_t i = tid; i < nw; i += gsz) p.ops_pool[off + i] = scratch[i];
+        }
+        __syncthreads();
+        if (p.stages == 2) {
+            stage ^= 1;
+        } else {
+            if (tid == 0) {
+                const uint32_t nxt = pop();
+                ctl->idx[0] = nxt;
+                if (nxt != kInvalidIdx) issue_load(0, nxt);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+size_t banded_smem_bytes(int A, int win, int seq_words, int stages)
+{
+    const size_t row_bytes = (size_t)((win + 7) & ~7) * 2;
+    const size_t ring_bytes = (3 * (size_t)A * row_bytes + 15) & ~(size_t)15;
+    const size_t lohi_bytes = ((3 * (size_t)A * 2 * sizeof(int)) + 15) & ~(size_t)15;
+    return ring_bytes + lohi_bytes + 2 * (size_t)stages * seq_words * 4 + sizeof(BandCtl) + 16;
+}
+
+template <bool ASCII, bool BT>
+static cudaError_t launch_banded_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
+{
+    auto kfn = wfa_banded_kernel<ASCII, BT>;
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kfn<<<ctas, threads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool ASCII, bool BT>
+static int occupancy_banded_one(int threads, size_t smem)
+{
+    auto kfn = wfa_banded_kernel<ASCII, BT>;
+    int n = 0;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
+    return n;
+}
+
+cudaError_t launch_banded(const KernelParams &p, int threads, int ctas, size_t smem_bytes, bool ascii, cudaStream_t s)
+{
+    const bool bt = p.with_bt != 0;
+    if (ascii) return bt ? launch_banded_one<true, true>(p, threads, ctas, smem_bytes, s)
+                         : launch_banded_one<true, false>(p, threads, ctas, smem_bytes, s);
+    return bt ? launch_banded_one<false, true>(p, threads, ctas, smem_bytes, s)
+              : launch_banded_one<false, false>(p, threads, ctas, smem_bytes, s);
+}
+
+int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii, bool bt)
+{
+    if (ascii) return bt ? occupancy_banded_one<true, true>(threads, smem_bytes) : occupancy_banded_one<true, false>(threads, smem_bytes);
+    return bt ? occupancy_banded_one<false, true>(threads, smem_bytes) : occupancy_banded_one<false, false>(threads, smem_bytes);
+}
+
 /* ---- host-side launch helpers ---------------------------------------------- */
 
 template <bool WARP, bool ASCII, bool BT>

@@ -46,6 +46,10 @@ struct KernelParams {
     int center;                   /* index of k = 0 inside a row                             */
     int seq_words;                /* u32 capacity of one packed sequence buffer in smem      */
     int with_bt;
+    int band;                     /* banded kernel: re-centre every `band` scores           */
+    int win;                      /* banded kernel: window width in diagonals               */
+    int32_t *band_lo;             /* banded kernel: per group, lo of every score (traceback) */
+    uint32_t band_lo_words;
     int stages;                   /* 1 or 2 sequence buffers per group (2 = prefetch next pair) */
     /* decision arena: one region per worker group */
     uint4 *arena;
@@ -76,6 +80,10 @@ void launch_pack(const PackParams &p, cudaStream_t s);
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
                          size_t smem_bytes, bool ascii_extend, cudaStream_t s);
 size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages);
+cudaError_t launch_banded(const KernelParams &p, int threads, int ctas, size_t smem_bytes, bool ascii_extend,
+                          cudaStream_t s);
+size_t banded_smem_bytes(int A, int win, int seq_words, int stages);
+int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii_extend, bool with_bt);
 int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend, bool with_bt);
 
 } // namespace wfagpu
