@@ -110,7 +110,7 @@ def cells_of_scores(lib, wfagpu, scores):
     md = MAX_ERROR * (max(x, o + e) + 1) + 16
     tab = (wfagpu.Step * (md + 1))()
     units = C.c_uint64()
-    d_end = lib.wfagpu_build_step_table(x, o, e, MAX_ERROR, md, tab, C.byref(units))
+    d_end = lib.wfagpu_build_step_table(x, o, e, MAX_ERROR, md, 0, tab, C.byref(units))
     cum = [0] * (d_end + 1)
     run = 0
     for d in range(d_end):

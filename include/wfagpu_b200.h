@@ -36,8 +36,11 @@ typedef struct {
 /* Builds the table for scores 0 .. d_end-1 (returns d_end; tab may be NULL to
  * size it).  `arena_units` receives the number of 16-byte decision units one
  * alignment can write.  Budget rule = reference: MDI steps stop once
- * steps >= max_steps-1 (sequence_alignment_kernel.cu:584, steps starts at 1). */
-int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist,
+ * steps >= max_steps-1 (sequence_alignment_kernel.cu:584, steps starts at 1).
+ * banded_win == 0: exact kernels (n = computed half width, row_off = bit-plane row);
+ * banded_win  > 0: banded kernels (n = number of M/I/D steps so far, rows of
+ * ceil(win/32) units). */
+int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist, int banded_win,
                             wfagpu_step_t *tab, uint64_t *arena_units);
 
 /* ------------------------------------------------------- device batches --- */

@@ -42,7 +42,7 @@ int km_build_steps(int x, int o, int e, int max_steps, int max_dist, km_step_t *
 {
     uint8_t *exM = (uint8_t *)calloc((size_t)max_dist + 1, 1);
     uint8_t *exI = (uint8_t *)calloc((size_t)max_dist + 1, 1);
-    int steps = 1, n = 0, d;
+    int steps = 1, n = 0, mdi = 0, d;
     uint64_t off = 0;
     exM[0] = 1;
     tab[0].kind = KM_KIND_M; tab[0].n = 0; tab[0].row_off = 0;
@@ -58,7 +58,9 @@ int km_build_steps(int x, int o, int e, int max_steps, int max_dist, km_step_t *
             tab[d].kind = KM_KIND_M; exM[d] = 1;
         } else {
             tab[d].kind = KM_KIND_MDI; exM[d] = 1; exI[d] = 1;
-            n++; steps++;
+            mdi++; steps++;
+            /* reachable diagonals: a gap of |k| bases costs at least o + |k| e */
+            { int reach = (d - o) / e; n = mdi < reach ? mdi : reach; if (n < 0) n = 0; }
         }
         tab[d].n = n;
         tab[d].row_off = (uint32_t)off;

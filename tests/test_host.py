@@ -99,7 +99,7 @@ def test_step_table_equals_model(lib, oracle, pen):
     ms = 300
     md = ms * (max(x, o + e) + 1) + 16
     t1 = (wfagpu.Step * (md + 1))(); u1 = C.c_uint64()
-    d1 = lib.wfagpu_build_step_table(x, o, e, ms, md, t1, C.byref(u1))
+    d1 = lib.wfagpu_build_step_table(x, o, e, ms, md, 0, t1, C.byref(u1))
     t2 = (KmStep * (md + 1))(); u2 = C.c_uint64()
     d2 = oracle.L.km_build_steps(x, o, e, ms, md, t2, C.byref(u2))
     assert d1 == d2 and u1.value * 4 == u2.value

@@ -115,7 +115,7 @@ struct Slot {
     PinBuf<uint32_t> h_counters;
     PinBuf<unsigned long long> h_cells;
     PinBuf<wfagpu_step_t> h_steps;
-    int tab_key[4] = {-1, -1, -1, -1};
+    int tab_key[5] = {-1, -1, -1, -1, -1};
     int tab_d_end = 0;
     uint64_t tab_arena_units = 0;
     size_t n = 0;
@@ -377,21 +377,24 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
 {
     /* step table for the full budget of this pass (cached per slot) */
     const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);
-    if (!(s.tab_key[0] == plan.x && s.tab_key[1] == plan.o && s.tab_key[2] == plan.e && s.tab_key[3] == max_steps)) {
+    const int tab_win = plan.band > 0 ? (plan.band_width > 0 ? plan.band_width : 512) : 0;
+    if (!(s.tab_key[0] == plan.x && s.tab_key[1] == plan.o && s.tab_key[2] == plan.e && s.tab_key[3] == max_steps &&
+          s.tab_key[4] == tab_win)) {
         if (s.h_steps.ensure((size_t)max_dist + 1)) return -1;
         CK(cudaStreamSynchronize(s.stream));  /* a previous pass may still be reading the pinned table */
         uint64_t units = 0;
-        const int de = wfagpu_build_step_table(plan.x, plan.o, plan.e, max_steps, max_dist, s.h_steps.p, &units);
+        const int de = wfagpu_build_step_table(plan.x, plan.o, plan.e, max_steps, max_dist, tab_win, s.h_steps.p, &units);
         if (de < 1) return -1;
         if (s.steps.ensure((size_t)de + 1)) return -1;
         CK(cudaMemcpyAsync(s.steps.p, s.h_steps.p, (size_t)de * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
-        s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = max_steps;
+        s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = max_steps; s.tab_key[4] = tab_win;
         s.tab_d_end = de;
         s.tab_arena_units = units;
     }
     const wfagpu_step_t *tab = s.h_steps.p;
     const int d_full = s.tab_d_end;
-    const int n_full = tab[d_full - 1].n;
+    int n_full = 0;
+    for (int dd = d_full - 1; dd >= 0 && dd >= d_full - 4; --dd) n_full = std::max(n_full, (int)tab[dd].n);
     /* half width to provision: the full budget, or (first pass only) what recent batches
      * with these penalties needed plus a margin -- pairs that outgrow it are re-dispatched */
     int n_want = n_full;
@@ -431,9 +434,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     /* scores this launch can reach and the decision units they need */
     int d_end = d_full;
     uint64_t arena_units = s.tab_arena_units;
-    if (banded) {
-        arena_units = (uint64_t)n_full * (uint64_t)((win + 31) >> 5);
-    } else if (c.n_cap < n_full) {
+    if (!banded && c.n_cap < n_full) {
         int lo = 0, hi = d_full;                     /* first score whose half width exceeds n_cap */
         while (lo < hi) {
             const int mid = (lo + hi) / 2;

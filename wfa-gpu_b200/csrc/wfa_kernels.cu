@@ -603,7 +603,6 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
     BandCtl *ctl = reinterpret_cast<BandCtl *>(smem_raw + ring_bytes + lohi_bytes + seq_total);
 
     const uint32_t group = blockIdx.x;
-    const uint32_t row_units = (uint32_t)((W + 31) >> 5);
     uint4 *const arena = p.arena + (size_t)group * p.arena_units;
     int32_t *const lo_tab = p.band_lo + (size_t)group * p.band_lo_words;
     uint32_t *const scratch = p.ops_scratch + (size_t)group * p.ops_scratch_words;
@@ -758,7 +757,7 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
                             LO[2 * A + sM] = lo; HI[2 * A + sM] = hi;
                             if (BT) lo_tab[d] = lo;
                         }
-                        uint4 *rp = arena + (size_t)((uint32_t)st.n - 1u) * row_units + warp;
+                        uint4 *rp = arena + st.row_off + warp;
                         const int width = hi - lo + 1;
                         for (int idc = tid; (idc - lane) < width; idc += gsz, rp += nwarps) {
                             bool bI = false, bD = false, bM0 = false, bM1 = false;
@@ -825,7 +824,7 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
                         if (st.kind != WFAGPU_STEP_MDI) { bad = true; break; }
                         const int ii = ck - lo_tab[cd];
                         if (ii < 0 || ii >= W) { bad = true; break; }
-                        const uint4 dec = arena[(size_t)((uint32_t)st.n - 1u) * row_units + (ii >> 5)];
+                        const uint4 dec = arena[st.row_off + (ii >> 5)];
                         const int b = ii & 31;
                         if (comp == 0) {
                             op = OP_SUB;

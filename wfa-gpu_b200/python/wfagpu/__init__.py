@@ -122,7 +122,7 @@ def load():
     L.wfagpu_last_run_stats.argtypes = [P(RunStats)]
     L.wfagpu_synth_add_pairs.argtypes = [P(AlignerStruct), C.c_uint64, C.c_size_t, C.c_int, C.c_double, C.c_double]
     L.wfagpu_synth_add_pairs.restype = C.c_bool
-    L.wfagpu_build_step_table.argtypes = [C.c_int] * 5 + [P(Step), P(C.c_uint64)]
+    L.wfagpu_build_step_table.argtypes = [C.c_int] * 6 + [P(Step), P(C.c_uint64)]
     L.wfagpu_ops_to_cigar.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int,
                                       P(C.c_uint32), C.c_uint32, P(Cigar)]
     L.wfagpu_ops_to_cigar.restype = C.c_bool
