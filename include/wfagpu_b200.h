@@ -20,6 +20,9 @@
 extern "C" {
 #endif
 
+/* Longest sequence wfagpu_add_sequences accepts (the reference: MAX_SEQ_LEN - 1 = 32767). */
+#define WFAGPU_MAX_SEQ_LEN ((size_t)1 << 22)
+
 /* ---------------------------------------------------------- step table --- */
 /* Per-score control record.  It depends on the penalties and the step budget
  * only (the existence logic of lib/kernels/sequence_alignment_kernel.cu:584-631

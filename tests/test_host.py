@@ -66,8 +66,9 @@ def test_api_argument_checks(lib):
     assert not a.initialize_parameters(-2, 3, 1)
     assert not a.initialize_parameters(0, 0, 0)
     assert a.initialize_parameters(2, 3, 1)
-    assert not a.add_sequences("A" * 32768, "ACGT")      # lib/aligner.c:139-142: max length 32767
-    assert a.add_sequences("A" * 32767, "ACGT")
+    assert a.add_sequences("A" * 32767, "ACGT")          # the reference's limit (lib/aligner.c:139-142) ...
+    assert a.add_sequences("A" * 40000, "ACGT")          # ... is lifted: long pairs run on the int32 tier
+    assert not a.add_sequences("A" * (1 << 22), "ACGT")
 
 
 def test_buffer_layout_and_defaults():

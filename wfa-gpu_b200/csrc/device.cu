@@ -91,6 +91,7 @@ struct LaunchCfg {
     int seq_words;
     size_t smem;
     int A, E1, G;
+    bool global_ring;     /* large tier: rings in global memory, int32 offsets */
 };
 
 struct Slot {
@@ -107,6 +108,7 @@ struct Slot {
     DevBuf<uint4> arena;
     DevBuf<uint32_t> scratch;
     DevBuf<int32_t> band_lo;
+    DevBuf<int32_t> gring;
     DevBuf<wfagpu_step_t> steps;
     PinBuf<wfagpu_pair_t> h_pairs;
     PinBuf<uint32_t> h_order;
@@ -140,6 +142,7 @@ struct wfagpu_device {
     int hint_dist = 0;
     int hint_key[3] = {-1, -1, -1};
     bool use_hint = true;
+    bool force_large = false;
 };
 
 static std::mutex g_mu;
@@ -192,6 +195,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->force_ctas_per_sm = env_int("WFAGPU_CTAS_PER_SM", 0);
     d->force_warp = env_int("WFAGPU_WARP_KERNEL", -1);
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
+    d->force_large = env_int("WFAGPU_FORCE_LARGE", 0) != 0;
     g_devices.push_back(d);
     return d;
 }
@@ -206,7 +210,7 @@ extern "C" void wfagpu_device_close_all(void)
             s.ascii.release(); s.packed.release(); s.pairs.release(); s.order.release();
             s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
             s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release();
-            s.scratch.release(); s.steps.release(); s.band_lo.release();
+            s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
             s.h_counters.release(); s.h_cells.release(); s.h_steps.release();
             for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -292,6 +296,31 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
     n_want = std::max(1, n_want);
     auto rs = [&](int ncap) { return 2 * (ncap + 2 * G + 1) + 2; };
 
+    c->global_ring = false;
+    bool large = d->force_large || max_len >= (1u << 15);
+    if (!large) {
+        /* rings that do not fit one CTA's shared memory even single-buffered go to the large tier */
+        if (exact_smem_bytes(A, E1, rs(n_want), seq_words, 1, 1) > smem_max) large = true;
+    }
+    if (large) {
+        c->global_ring = true;
+        c->groups_per_cta = 1;
+        c->stages = 1;
+        c->n_cap = n_want;
+        c->row_stride = rs(n_want);
+        c->center = n_want + 2 * G + 1;
+        c->smem = exact_smem_bytes(A, E1, 0, seq_words, 1, 1);     /* sequences + control only */
+        if (!ascii && c->smem > smem_max) {
+            fprintf(stderr, "[wfagpu] sequences of %u bases do not fit in shared memory; not supported yet\n", max_len);
+            return -2;
+        }
+        c->group_threads = d->force_threads ? d->force_threads : 512;
+        int occ = large_max_ctas_per_sm(c->group_threads, c->smem, ascii, bt);
+        if (occ < 1) return -1;
+        occ = std::min(occ, d->force_ctas_per_sm ? d->force_ctas_per_sm : 2);
+        c->ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ * d->prop.multiProcessorCount, n_items));
+        return 0;
+    }
     bool warp = (rs(n_want) <= 400) && max_len <= 1024;
     if (d->force_warp >= 0) warp = d->force_warp != 0;
 
@@ -445,8 +474,20 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     }
     *capped_out = c.n_cap < n_full;
 
-    const size_t groups = (size_t)c.ctas * c.groups_per_cta;
     if (!plan.with_cigar) arena_units = 0;
+    {
+        /* keep the decision arenas within a third of the free device memory: fewer, not smaller, groups */
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t have = s.arena.cap * sizeof(uint4);
+        const size_t budget = std::max<size_t>((free_b + have) / 3, (size_t)64 << 20);
+        const size_t per_group = (size_t)arena_units * sizeof(uint4) * (size_t)c.groups_per_cta + 1;
+        const size_t max_ctas = std::max<size_t>(1, budget / per_group);
+        if ((size_t)c.ctas > max_ctas) c.ctas = (int)max_ctas;
+    }
+    const size_t groups = (size_t)c.ctas * c.groups_per_cta;
+    const uint64_t gring_elems = c.global_ring ? (uint64_t)(c.A + 2 * c.E1) * (uint64_t)c.row_stride : 0;
+    if (s.gring.ensure(groups * gring_elems + 1)) return -1;
     const uint32_t scratch_words = plan.with_cigar ? (uint32_t)((2 * (size_t)d_end + 31) / 16 + 2) : 1;
     if (s.arena.ensure(groups * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
     const uint32_t band_lo_words = (banded && plan.with_cigar) ? (uint32_t)d_end + 1 : 0;
@@ -485,6 +526,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.win = win;
     kp.band_lo = s.band_lo.p;
     kp.band_lo_words = band_lo_words;
+    kp.gring = c.global_ring ? s.gring.p : nullptr;
+    kp.gring_elems = gring_elems;
     kp.arena = s.arena.p;
     kp.arena_units = arena_units;
     kp.ops_scratch = s.scratch.p;
@@ -499,9 +542,9 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.ascii_count = s.counters.p + CTR_ASCII;
     kp.cells = d->count_cells ? s.cells.p : nullptr;
     if (env_int("WFAGPU_VERBOSE", 0))
-        fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d arena=%.1f MB\n",
+        fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d band=%d tier=%s arena=%.1f MB\n",
                 n_items, max_steps, c.n_cap, d_end, c.group_threads, c.groups_per_cta, c.ctas, c.stages, c.smem,
-                (int)ascii, groups * arena_units * 16.0 / 1e6);
+                (int)ascii, plan.band > 0 ? win : 0, c.global_ring ? "global-int32" : "smem-int16", groups * arena_units * 16.0 / 1e6);
     cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
                            : launch_exact(kp, c.group_threads, c.groups_per_cta, c.ctas, c.smem, ascii, s.stream);
     if (e != cudaSuccess) {
@@ -567,7 +610,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
         while (pending > 0) {
             s.stats.redispatched += pending;
             long long next = capped ? steps : std::max<long long>(steps * 2, 64);
-            if (next > 30000) {
+            if (next > 60000) {
                 fprintf(stderr, "[wfagpu] %u pairs need more than %lld wavefront steps; not supported yet\n", pending, steps);
                 return -4;
             }

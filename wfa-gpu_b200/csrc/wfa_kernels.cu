@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackParams p)
     const uint32_t ngroups = (len + (4u - (len & 3u))) >> 2;
     /* number of aligned uint4 that may be touched without leaving the batch buffer */
     const uint32_t n16 = (uint32_t)(((addr & 15) + len + 1 + 15) >> 4);
-    bool flag = (len >= (1u << 15));
+    bool flag = false;   /* (the reference also flags len >= 32768 because of its int16 offsets; the large tier takes those) */
 
     for (uint32_t it = 0; it * 64u < nwords_pad; ++it) {
         const uint32_t u = it * 32u + lane;                     /* index of this lane's first uint4 */
@@ -179,6 +179,30 @@ __device__ __forceinline__ void sts_16(uint32_t a, int v)
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory");
 }
 
+/* Where the wavefront rings live.  RingS16: shared memory, int16 offsets (sequences
+ * < 32768 bases, the reference's wfa_offset_t).  RingG32: global memory (L2), int32
+ * offsets -- the large tier for wavefronts wider than an SM's shared memory and for
+ * sequences the reference cannot take at all (>= 32768 bases, lib/wfa_types.h:28-32). */
+struct RingS16 {
+    using addr_t = uint32_t;                       /* shared-window address of diagonal 0 of a row */
+    static constexpr int kNull = kOffNull;
+    static constexpr uint32_t kElem = 2;
+    __device__ static __forceinline__ int ld(addr_t row, int k) { return lds_s16(row + (uint32_t)(2 * k)); }
+    __device__ static __forceinline__ void st(addr_t row, int k, int v) { sts_16(row + (uint32_t)(2 * k), v); }
+    __device__ static __forceinline__ addr_t add(addr_t a, uint32_t bytes) { return a + bytes; }
+};
+struct RingG32 {
+    using addr_t = int32_t *;
+    static constexpr int kNull = -(1 << 28);
+    static constexpr uint32_t kElem = 4;
+    __device__ static __forceinline__ int ld(addr_t row, int k) { return row[k]; }
+    __device__ static __forceinline__ void st(addr_t row, int k, int v) { row[k] = v; }
+    __device__ static __forceinline__ addr_t add(addr_t a, uint32_t bytes)
+    {
+        return reinterpret_cast<addr_t>(reinterpret_cast<char *>(a) + bytes);
+    }
+};
+
 template <bool WARP>
 struct Group {
     __device__ static __forceinline__ int tid() { return WARP ? (threadIdx.x & 31) : threadIdx.x; }
@@ -195,11 +219,12 @@ struct Group {
  * on 32-bit windows.  With the 8-base stride layout a window of >= 9 bases
  * starts inside one word, so the common case (a mismatch within 9 bases) costs
  * two shared loads and no loop. */
-__device__ __forceinline__ int extend_packed(uint32_t Pa, uint32_t Ta, int plen, int tlen, int k, int off)
+__device__ __forceinline__ int extend_packed(uint32_t Pa, uint32_t Ta, int plen, int tlen, int k, int off,
+                                             const int null_v = kOffNull)
 {
     const int v = off - k, h = off;
     const int rem = min(plen - v, tlen - h);
-    if (rem < 0) return kOffNull;
+    if (rem < 0) return null_v;
     const uint32_t uv = (uint32_t)v, uh = (uint32_t)h;
     const uint32_t wp = lds_u32(Pa + ((uv >> 3) << 2)) << ((uv & 7u) * 2u);
     const uint32_t wt = lds_u32(Ta + ((uh >> 3) << 2)) << ((uh & 7u) * 2u);
@@ -226,11 +251,11 @@ __device__ __forceinline__ int extend_packed(uint32_t Pa, uint32_t Ta, int plen,
  * byte equality like the CPU WFA the reference falls back to
  * (utils/wfa_cpu.c:57-85), straight from the ASCII copy in global memory. */
 __device__ __forceinline__ int extend_ascii(const char *__restrict__ P, const char *__restrict__ T, int plen,
-                                            int tlen, int k, int off)
+                                            int tlen, int k, int off, const int null_v = kOffNull)
 {
     const int v = off - k, h = off;
     const int rem = min(plen - v, tlen - h);
-    if (rem < 0) return kOffNull;
+    if (rem < 0) return null_v;
     int acc = 0;
     while (acc < rem && P[v + acc] == T[h + acc]) ++acc;
     return off + acc;
@@ -243,10 +268,13 @@ struct GroupCtl {
     uint32_t ops_off;
 };
 
-template <bool WARP, bool ASCII, bool BT>
+template <bool WARP, bool ASCII, bool BT, typename R>
 __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const __grid_constant__ KernelParams p)
 {
     using G = Group<WARP>;
+    using RA = typename R::addr_t;
+    constexpr bool GR = (R::kElem == 4);          /* rings in global memory */
+    constexpr int NULLV = R::kNull;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int tid = G::tid();
@@ -259,8 +287,8 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
 
     /* ---- carve shared memory: [rings][sequence stages][ctl] per group ---- */
     const int rows = p.A + 2 * p.E1;
-    const uint32_t row_bytes = (uint32_t)p.row_stride * 2u;
-    const uint32_t ring_bytes = ((uint32_t)rows * row_bytes + 15u) & ~15u;
+    const uint32_t row_bytes = (uint32_t)p.row_stride * R::kElem;
+    const uint32_t ring_bytes = GR ? 0u : (((uint32_t)rows * row_bytes + 15u) & ~15u);
     const uint32_t seq_bytes = (uint32_t)p.seq_words * 4u;          /* one sequence, one stage */
     const uint32_t seq_total = ASCII ? 0u : 2u * (uint32_t)p.stages * seq_bytes;
     const uint32_t group_bytes = (ring_bytes + seq_total + (uint32_t)sizeof(GroupCtl) + 15u) & ~15u;
@@ -271,9 +299,14 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
 
     const int x = p.x, e = p.e, A = p.A, E1 = p.E1, GW = p.G;
     const int oe = p.o + p.e;
-    const uint32_t M0 = ring_sa + 2u * (uint32_t)p.center;          /* row 0 of M, diagonal 0 */
-    const uint32_t I0 = M0 + (uint32_t)A * row_bytes;
-    const uint32_t D0 = I0 + (uint32_t)E1 * row_bytes;
+    RA M0;                                                          /* row 0 of M, diagonal 0 */
+    if constexpr (GR) {
+        M0 = reinterpret_cast<RA>(p.gring + (size_t)group * p.gring_elems + p.center);
+    } else {
+        M0 = (RA)(ring_sa + 2u * (uint32_t)p.center);
+    }
+    const RA I0 = R::add(M0, (uint32_t)A * row_bytes);
+    const RA D0 = R::add(I0, (uint32_t)E1 * row_bytes);
 
     uint4 *const arena = p.arena + (size_t)group * p.arena_units;
     uint32_t *const scratch = p.ops_scratch + (size_t)group * p.ops_scratch_words;
@@ -329,8 +362,8 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         const char *const Pg = p.ascii + pr.p_ascii;
         const char *const Tg = p.ascii + pr.t_ascii;
         auto extend = [&](int k, int off) -> int {
-            if (ASCII) return extend_ascii(Pg, Tg, plen, tlen, k, off);
-            return extend_packed(Pa, Ta, plen, tlen, k, off);
+            if (ASCII) return extend_ascii(Pg, Tg, plen, tlen, k, off, NULLV);
+            return extend_packed(Pa, Ta, plen, tlen, k, off, NULLV);
         };
 
         /* pairs flagged by the packer are left to the byte-compare launch */
@@ -343,7 +376,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
             for (int i = tid; i < total; i += gsz) {
                 const int r = i / span;
                 const int k = i - r * span - 2 * GW;
-                sts_16(M0 + (uint32_t)r * row_bytes + (uint32_t)(2 * k), kOffNull);
+                R::st(R::add(M0, (uint32_t)r * row_bytes), k, NULLV);
             }
         }
         if (!ASCII) mbar_wait(&ctl->bar[stage], (phase_bits >> stage) & 1u);
@@ -354,63 +387,63 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         bool finished = false;
 
         if (!skip) {
-            if (tid == 0) sts_16(M0, extend(0, 0));
+            if (tid == 0) R::st(M0, 0, extend(0, 0));
             G::sync();
-            if (kt == 0 && lds_s16(M0) == tlen) {
+            if (kt == 0 && R::ld(M0, 0) == tlen) {
                 finished = true;
             } else {
                 wfagpu_step_t st_next = p.steps[1 < p.d_end ? 1 : 0];
                 /* Row addresses of the current score and of its sources are carried from
                  * score to score (one add + wrap each) so that the diagonal loop sees them
                  * as plain live values instead of re-deriving them. */
-                const uint32_t Mend = M0 + (uint32_t)A * row_bytes;
-                const uint32_t Iend = I0 + (uint32_t)E1 * row_bytes;
-                const uint32_t Dend = D0 + (uint32_t)E1 * row_bytes;
-                uint32_t aMc = M0, aIc = I0, aDc = D0;                      /* rows of score d (d = 0 now) */
-                uint32_t aMx = M0 + (uint32_t)((A - x % A) % A) * row_bytes;     /* row of score d - x     */
-                uint32_t aMo = M0 + (uint32_t)((A - oe % A) % A) * row_bytes;    /* row of score d - o - e */
-                uint32_t aIe = I0 + (uint32_t)((E1 - e % E1) % E1) * row_bytes;  /* row of score d - e     */
-                uint32_t aDe = D0 + (uint32_t)((E1 - e % E1) % E1) * row_bytes;
+                const RA Mend = R::add(M0, (uint32_t)A * row_bytes);
+                const RA Iend = R::add(I0, (uint32_t)E1 * row_bytes);
+                const RA Dend = R::add(D0, (uint32_t)E1 * row_bytes);
+                RA aMc = M0, aIc = I0, aDc = D0;                                    /* rows of score d (d = 0 now) */
+                RA aMx = R::add(M0, (uint32_t)((A - x % A) % A) * row_bytes);       /* row of score d - x     */
+                RA aMo = R::add(M0, (uint32_t)((A - oe % A) % A) * row_bytes);      /* row of score d - o - e */
+                RA aIe = R::add(I0, (uint32_t)((E1 - e % E1) % E1) * row_bytes);    /* row of score d - e     */
+                RA aDe = R::add(D0, (uint32_t)((E1 - e % E1) % E1) * row_bytes);
                 for (int d = 1; d < p.d_end; ++d) {
                     const wfagpu_step_t st = st_next;
                     if (d + 1 < p.d_end) st_next = p.steps[d + 1];
                     const int n = st.n;
                     if (n > p.n_cap) break;
-                    aMc += row_bytes; if (aMc == Mend) aMc = M0;
-                    aMx += row_bytes; if (aMx == Mend) aMx = M0;
-                    aMo += row_bytes; if (aMo == Mend) aMo = M0;
-                    aIc += row_bytes; if (aIc == Iend) aIc = I0;
-                    aIe += row_bytes; if (aIe == Iend) aIe = I0;
-                    aDc += row_bytes; if (aDc == Dend) aDc = D0;
-                    aDe += row_bytes; if (aDe == Dend) aDe = D0;
+                    aMc = R::add(aMc, row_bytes); if (aMc == Mend) aMc = M0;
+                    aMx = R::add(aMx, row_bytes); if (aMx == Mend) aMx = M0;
+                    aMo = R::add(aMo, row_bytes); if (aMo == Mend) aMo = M0;
+                    aIc = R::add(aIc, row_bytes); if (aIc == Iend) aIc = I0;
+                    aIe = R::add(aIe, row_bytes); if (aIe == Iend) aIe = I0;
+                    aDc = R::add(aDc, row_bytes); if (aDc == Dend) aDc = D0;
+                    aDe = R::add(aDe, row_bytes); if (aDe == Dend) aDe = D0;
 
                     if (st.kind == WFAGPU_STEP_NULL) {
                         for (int k = -n - GW + tid; k <= n + GW; k += gsz) {
-                            sts_16(aMc + (uint32_t)(2 * k), kOffNull);
-                            sts_16(aIc + (uint32_t)(2 * k), kOffNull);
-                            sts_16(aDc + (uint32_t)(2 * k), kOffNull);
+                            R::st(aMc, k, NULLV);
+                            R::st(aIc, k, NULLV);
+                            R::st(aDc, k, NULLV);
                         }
                         G::sync();
                         continue;
                     }
                     if (st.kind == WFAGPU_STEP_M) {
                         for (int k = -n - GW + tid; k <= n + GW; k += gsz) {
-                            sts_16(aIc + (uint32_t)(2 * k), kOffNull);
-                            sts_16(aDc + (uint32_t)(2 * k), kOffNull);
-                            int m = kOffNull;
+                            R::st(aIc, k, NULLV);
+                            R::st(aDc, k, NULLV);
+                            int m = NULLV;
                             if (k >= -n && k <= n) {
-                                m = lds_s16(aMx + (uint32_t)(2 * k)) + 1;
+                                m = R::ld(aMx, k) + 1;
                                 if (m >= 0) m = extend(k, m);
                             }
-                            sts_16(aMc + (uint32_t)(2 * k), m);
+                            R::st(aMc, k, m);
                         }
                     } else {
                         /* guard cells: NULL on both sides of [-n, n] */
                         for (int g = tid; g < 2 * GW; g += gsz) {
                             const int k = (g < GW) ? (-n - 1 - g) : (n + 1 + (g - GW));
-                            sts_16(aMc + (uint32_t)(2 * k), kOffNull);
-                            sts_16(aIc + (uint32_t)(2 * k), kOffNull);
-                            sts_16(aDc + (uint32_t)(2 * k), kOffNull);
+                            R::st(aMc, k, NULLV);
+                            R::st(aIc, k, NULLV);
+                            R::st(aDc, k, NULLV);
                         }
                         const int width = 2 * n + 1;
                         uint4 *rp = arena + st.row_off + warp_in_group;
@@ -419,12 +452,11 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                             bool bI = false, bD = false, bM0 = false, bM1 = false;
                             if (idc < width) {
                                 const int k = idc - n;
-                                const uint32_t kk = (uint32_t)(2 * k);
-                                const int io = lds_s16(aMo + kk - 2u) + 1;
-                                const int ie = lds_s16(aIe + kk - 2u) + 1;
-                                const int dopen = lds_s16(aMo + kk + 2u);
-                                const int dext = lds_s16(aDe + kk + 2u);
-                                const int X = lds_s16(aMx + kk) + 1;
+                                const int io = R::ld(aMo, k - 1) + 1;
+                                const int ie = R::ld(aIe, k - 1) + 1;
+                                const int dopen = R::ld(aMo, k + 1);
+                                const int dext = R::ld(aDe, k + 1);
+                                const int X = R::ld(aMx, k) + 1;
                                 const int I = max(io, ie);
                                 const int D = max(dopen, dext);
                                 bI = ie >= io;                         /* extend beats open on ties */
@@ -434,9 +466,9 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                                 const int pM = max(max(X4, D * 4 + 3), I4);
                                 int M = pM >> 2;
                                 if (M >= 0) M = extend(k, M);
-                                sts_16(aIc + kk, I);
-                                sts_16(aDc + kk, D);
-                                sts_16(aMc + kk, M);
+                                R::st(aIc, k, I);
+                                R::st(aDc, k, D);
+                                R::st(aMc, k, M);
                                 bM0 = pM != X4;                        /* winner is I(1) or D(3) */
                                 bM1 = pM != I4;                        /* winner is X(2) or D(3) */
                             }
@@ -450,7 +482,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                         }
                     }
                     G::sync();
-                    if (kt >= -n && kt <= n && lds_s16(aMc + (uint32_t)(2 * kt)) == tlen) {
+                    if (kt >= -n && kt <= n && R::ld(aMc, kt) == tlen) {
                         finished = true;
                         dist = d;
                         break;
@@ -935,20 +967,20 @@ int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii, bool bt)
 
 /* ---- host-side launch helpers ---------------------------------------------- */
 
-template <bool WARP, bool ASCII, bool BT>
+template <bool WARP, bool ASCII, bool BT, typename R = RingS16>
 static cudaError_t launch_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
-    auto kfn = wfa_exact_kernel<WARP, ASCII, BT>;
+    auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R>;
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, threads, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-template <bool WARP, bool ASCII, bool BT>
+template <bool WARP, bool ASCII, bool BT, typename R = RingS16>
 static int occupancy_one(int threads, size_t smem)
 {
-    auto kfn = wfa_exact_kernel<WARP, ASCII, BT>;
+    auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R>;
     int n = 0;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
@@ -976,7 +1008,22 @@ cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_pe
     const bool warp = (group_threads == 32);
     const bool bt = p.with_bt != 0;
     const int threads = warp ? 32 * groups_per_cta : group_threads;
+    if (p.gring) {
+        /* large tier: CTA per pair, rings in global memory, int32 offsets */
+        if (ascii) return bt ? launch_one<false, true, true, RingG32>(p, threads, ctas, smem_bytes, s)
+                             : launch_one<false, true, false, RingG32>(p, threads, ctas, smem_bytes, s);
+        return bt ? launch_one<false, false, true, RingG32>(p, threads, ctas, smem_bytes, s)
+                  : launch_one<false, false, false, RingG32>(p, threads, ctas, smem_bytes, s);
+    }
     return WFAGPU_DISPATCH(launch_one, p, threads, ctas, smem_bytes, s);
+}
+
+int large_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii, bool bt)
+{
+    if (ascii) return bt ? occupancy_one<false, true, true, RingG32>(threads, smem_bytes)
+                         : occupancy_one<false, true, false, RingG32>(threads, smem_bytes);
+    return bt ? occupancy_one<false, false, true, RingG32>(threads, smem_bytes)
+              : occupancy_one<false, false, false, RingG32>(threads, smem_bytes);
 }
 
 int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii, bool bt)

@@ -52,6 +52,8 @@ struct KernelParams {
     uint32_t band_lo_words;
     int stages;                   /* 1 or 2 sequence buffers per group (2 = prefetch next pair) */
     /* decision arena: one region per worker group */
+    int32_t *gring;               /* large tier: per-group rings in global memory, else null */
+    uint64_t gring_elems;         /* int32 elements per group                                */
     uint4 *arena;
     uint64_t arena_units;         /* uint4 units per group                                   */
     uint32_t *ops_scratch;        /* per-group scratch for the traceback's op words          */
@@ -84,6 +86,7 @@ cudaError_t launch_banded(const KernelParams &p, int threads, int ctas, size_t s
                           cudaStream_t s);
 size_t banded_smem_bytes(int A, int win, int seq_words, int stages);
 int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii_extend, bool with_bt);
+int large_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii_extend, bool with_bt);
 int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend, bool with_bt);
 
 } // namespace wfagpu

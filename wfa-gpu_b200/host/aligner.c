@@ -103,10 +103,12 @@ bool wfagpu_add_sequences(wfagpu_aligner_t *aligner, const char *query, const ch
         const sequence_pair_t *last = &aligner->sequences_metadata[aligner->last_sequence_pair_idx];
         p_off = WFA_ALIGN_32_BITS(last->text_offset + last->text_len + 1);
     }
-    const size_t plen = strnlen(query, MAX_SEQ_LEN);
-    const size_t tlen = strnlen(target, MAX_SEQ_LEN);
-    if (plen >= MAX_SEQ_LEN || tlen >= MAX_SEQ_LEN) {
-        WARN("Sequences must be shorter than %lu.", MAX_SEQ_LEN - 1);
+    /* The reference stops at MAX_SEQ_LEN - 1 = 32767 bases (int16 offsets, lib/aligner.c:139-142).
+     * Longer sequences are accepted here and run on the int32 large tier. */
+    const size_t plen = strnlen(query, WFAGPU_MAX_SEQ_LEN);
+    const size_t tlen = strnlen(target, WFAGPU_MAX_SEQ_LEN);
+    if (plen >= WFAGPU_MAX_SEQ_LEN || tlen >= WFAGPU_MAX_SEQ_LEN) {
+        WARN("Sequences must be shorter than %lu.", (unsigned long)WFAGPU_MAX_SEQ_LEN - 1);
         return false;
     }
     const size_t t_off = WFA_ALIGN_32_BITS(p_off + plen + 1);

@@ -29,7 +29,7 @@ bool wfagpu_synth_add_pairs(wfagpu_aligner_t *aligner, uint64_t seed, size_t n, 
                             double err_lo, double err_hi)
 {
     static const char alphabet[4] = {'A', 'C', 'G', 'T'};
-    if (!aligner || length < 0 || length >= (int)MAX_SEQ_LEN) return false;
+    if (!aligner || length < 0 || (size_t)length * 2 >= WFAGPU_MAX_SEQ_LEN) return false;
     const size_t cap = (size_t)length * 2 + 64;
     char *text = (char *)malloc(cap);
     char *pattern = (char *)malloc(cap);
@@ -69,7 +69,6 @@ bool wfagpu_synth_add_pairs(wfagpu_aligner_t *aligner, uint64_t seed, size_t n, 
             }
         }
         pattern[plen] = 0;
-        if (plen >= (int)MAX_SEQ_LEN) { pattern[MAX_SEQ_LEN - 1] = 0; }
         ok = wfagpu_add_sequences(aligner, pattern, text);
     }
     free(text);
