@@ -86,6 +86,26 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def shard_seed(rank):
+    """Every rank aligns its own deterministic slice of the synthetic workload."""
+    return SEED + 7919 * rank
+
+
+def reduce_max(values, device=None):
+    """Max over ranks of a list of floats (device time, wall time): the slowest rank sets the pace."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def aggregate_value(pairs_per_gpu, world, steps, t_max):
+    """Whole-job throughput: all pairs of all ranks over the slowest rank's time."""
+    return pairs_per_gpu * world * steps / t_max
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -137,7 +157,7 @@ def run_ours(args):
     wfagpu.set_devices(str(local))
 
     a = wfagpu.Aligner()
-    a.add_synthetic(SEED + 7919 * rank, PAIRS_PER_GPU, LENGTH, ERR, ERR)
+    a.add_synthetic(shard_seed(rank), PAIRS_PER_GPU, LENGTH, ERR, ERR)
     assert a.initialize_parameters(*PEN)
     a.options.max_error = MAX_ERROR
     a.options.compute_cigar = True
@@ -178,12 +198,9 @@ def run_ours(args):
     n_ops_total = sum(out[i].n_ops for i in range(rb.n))
     assert all(out[i].status & 1 for i in range(rb.n)), "unfinished pairs in the benchmark batch"
 
-    t_dev = torch.tensor([dev_ms / 1e3, wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    t_max, wall_max = t_dev.tolist()
+    t_max, wall_max = reduce_max([dev_ms / 1e3, wall], device="cuda")
     total_pairs = PAIRS_PER_GPU * world * args.steps
-    value = total_pairs / t_max
+    value = aggregate_value(PAIRS_PER_GPU, world, args.steps, t_max)
 
     # ---------------- end to end through the public C API: `e2e` -------------
     a.pin_host_buffers()
@@ -198,10 +215,8 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     rs = a.run_stats()
-    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = total_pairs / t_e2e.item()
+    (t_e2e_max,) = reduce_max([e2e_s], device="cuda")
+    e2e_value = total_pairs / t_e2e_max
     # the e2e answer must be the resident answer
     assert [a.error(i) for i in range(0, a.num_pairs, 97)] == scores[::97]
 
@@ -247,7 +262,7 @@ def run_ours(args):
         "wall_ms_per_step": round(wall_max * 1e3 / args.steps, 3),
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(rs["h2d_bytes"]), "d2h_bytes_per_step": int(rs["d2h_bytes"]),
-                "gcups": round(gcells_total * world * args.steps / t_e2e.item() / 1e9, 1),
+                "gcups": round(gcells_total * world * args.steps / t_e2e_max / 1e9, 1),
                 "api": "wfagpu_align (page-locked host buffers, CIGAR text generated on the host)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks, "roofline": roofline, "roofline_int": roofline_int,

@@ -153,6 +153,10 @@ bool wfagpu_ops_to_cigar(const char *pattern, size_t plen, const char *text, siz
  * ("n:4").  Default (NULL/unset): environment WFAGPU_DEVICES, else device 0. */
 void wfagpu_set_devices(const char *spec);
 
+/* Chunking of a job over `n_devices` GPUs (pure function, used by launch_alignments*). */
+void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii_span,
+                        size_t *chunk_out, size_t *n_chunks_out);
+
 /* Stats of the last launch_alignments* call (summed over batches/devices). */
 typedef struct {
     double wall_s;
@@ -165,10 +169,24 @@ typedef struct {
     int devices;
 } wfagpu_run_stats_t;
 void wfagpu_last_run_stats(wfagpu_run_stats_t *st);
+/* false when the last launch_alignments* call failed on the GPU (nothing is computed on the CPU) */
+bool wfagpu_last_launch_ok(void);
 
 /* Clears errors and CIGAR text of a previous wfagpu_align (the reference, like
  * this library, appends to results[i].cigar) so an aligner can be re-aligned. */
 void wfagpu_reset_results(wfagpu_aligner_t *aligner);
+
+/* CLI input formats (replace utils/sequence_reader.c:137-392): append the pairs of a .seq file
+ * (">pattern" / "<text" lines) or of two FASTA files (n-th query record with n-th target record)
+ * to the aligner. max_pairs == 0 reads everything. Return the number of pairs, -1 on error. */
+long wfagpu_read_seq_file(wfagpu_aligner_t *aligner, const char *path, size_t max_pairs);
+long wfagpu_read_fasta_files(wfagpu_aligner_t *aligner, const char *query_path, const char *target_path,
+                             size_t max_pairs);
+
+/* `-c`: true iff `cigar` is a valid global alignment of (pattern, text) whose gap-affine cost is
+ * `error` (replaces check_cigar_edit + check_affine_distance, utils/verification.c:27-146). */
+bool wfagpu_check_result(const char *pattern, size_t plen, const char *text, size_t tlen,
+                         affine_penalties_t pen, unsigned int error, const char *cigar);
 
 /* Deterministic synthetic pairs (text uniform over ACGT, pattern =
  * text with ceil(L*err) edits, each uniformly mismatch / 1-base deletion /

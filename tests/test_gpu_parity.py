@@ -112,3 +112,21 @@ def test_banded_equals_oracle(oracle, cigar, specs, pen, band, window, max_error
         n_subopt += exact["distance"] != a.error(i)
     assert bad == []
     assert n_subopt <= a.num_pairs // 2
+
+
+def test_multi_gpu_sharding_matches_single_gpu(lib):
+    import ctypes as C
+    n = C.c_int(0)
+    lib.get_num_cuda_devices(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    specs = [(3000, 300, 0.05, 0.05), (200, 3000, 0.05, 0.05)]
+    wfagpu.set_devices("0")
+    a = run(specs, (2, 3, 1), True, max_error=600, batch=400)
+    wfagpu.set_devices("all")
+    b = run(specs, (2, 3, 1), True, max_error=600, batch=400)
+    st = b.run_stats()
+    wfagpu.set_devices("0")
+    assert st["devices"] >= 2
+    assert a.errors() == b.errors()
+    assert a.cigars() == b.cigars()

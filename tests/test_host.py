@@ -167,3 +167,35 @@ def test_no_cpu_fallback_without_gpu(lib):
     assert a.initialize_parameters(2, 3, 1)
     with pytest.raises(RuntimeError):
         a.align()
+
+
+def test_readers_seq_and_fasta(tmp_path, lib):
+    # utils/sequence_reader.c:137-392: .seq (blank lines skipped) and paired multi-line FASTA
+    seq = tmp_path / "a.seq"
+    seq.write_text(">ACGT\n<ACGA\n\n>TTTTT\n<TTT\n>GATTACA\n<GATTACA")       # no trailing newline on purpose
+    a = wfagpu.Aligner()
+    assert a.read_seq_file(str(seq)) == 3
+    assert [a.pair(i) for i in range(3)] == [("ACGT", "ACGA"), ("TTTTT", "TTT"), ("GATTACA", "GATTACA")]
+    b = wfagpu.Aligner()
+    assert b.read_seq_file(str(seq), 2) == 2 and b.num_pairs == 2
+    q = tmp_path / "q.fasta"
+    t = tmp_path / "t.fasta"
+    q.write_text(">q1 desc\nACGT\nACGT\n\n>q2\nTTTT\n")
+    t.write_text(" >t1\nACGTAC\nGT\n>t2\nTT\nTA\n")
+    c = wfagpu.Aligner()
+    assert c.read_fasta_files(str(q), str(t)) == 2
+    assert [c.pair(i) for i in range(2)] == [("ACGTACGT", "ACGTACGT"), ("TTTT", "TTTA")]
+    bad = tmp_path / "bad.seq"
+    bad.write_text("ACGT\n<ACGT\n")
+    d = wfagpu.Aligner()
+    assert d.read_seq_file(str(bad)) == -1
+
+
+def test_check_result(lib, oracle):
+    pen = wfagpu.AffinePenalties(2, 3, 1)
+    p, t = b"ACGTACGTAC", b"ACGTTCGAC"
+    r = oracle.align(p.decode(), t.decode(), 2, 3, 1, 100)
+    assert lib.wfagpu_check_result(p, len(p), t, len(t), pen, r["distance"], r["cigar"].encode())
+    assert not lib.wfagpu_check_result(p, len(p), t, len(t), pen, r["distance"] + 1, r["cigar"].encode())
+    assert not lib.wfagpu_check_result(p, len(p), t, len(t), pen, 0, b"9M")
+    assert not lib.wfagpu_check_result(p, len(p), t, len(t), pen, 0, b"garbage")

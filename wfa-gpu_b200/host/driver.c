@@ -278,6 +278,26 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* How the pair range is cut: chunks of at most `batch_size` pairs; with several GPUs at
+ * least two chunks per GPU so that the tail balances; a chunk's ASCII stays below the
+ * 32-bit offset limit of the device descriptors. */
+void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii_span,
+                        size_t *chunk_out, size_t *n_chunks_out)
+{
+    size_t chunk = batch_size;
+    if (n == 0) { *chunk_out = 0; *n_chunks_out = 0; return; }
+    if (chunk == 0 || chunk > n) chunk = n;
+    if (n_devices > 1) {
+        const size_t per = (n + (size_t)n_devices * 2 - 1) / ((size_t)n_devices * 2);
+        if (per > 0 && per < chunk) chunk = per;
+    }
+    const size_t avg = ascii_span / n + 1;
+    const size_t max_pairs = ((size_t)3 << 30) / avg;
+    if (max_pairs > 0 && chunk > max_pairs) chunk = max_pairs;
+    *chunk_out = chunk;
+    *n_chunks_out = (n + chunk - 1) / chunk;
+}
+
 static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_alignment_result_t *res,
                     wfa_alignment_options_t opt, bool cigar, bool check)
 {
@@ -300,20 +320,9 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     memset(&job, 0, sizeof(job));
     job.buf = buf; job.buf_size = buf_size; job.meta = meta; job.res = res; job.opt = opt; job.cigar = cigar;
     job.n = opt.num_alignments;
-    size_t chunk = opt.batch_size;
-    if (chunk == 0 || chunk > job.n) chunk = job.n;
-    if (ndev > 1) {
-        /* enough chunks for every GPU to get work and for the tail to balance */
-        const size_t per = (job.n + (size_t)ndev * 2 - 1) / ((size_t)ndev * 2);
-        if (per > 0 && per < chunk) chunk = per;
-    }
-    /* keep a chunk's ASCII below the 32-bit offset limit */
-    {
-        const size_t span = meta[job.n - 1].text_offset + meta[job.n - 1].text_len + 1 - meta[0].pattern_offset;
-        const size_t avg = span / job.n + 1;
-        const size_t max_pairs = ((size_t)3 << 30) / avg;
-        if (max_pairs > 0 && chunk > max_pairs) chunk = max_pairs;
-    }
+    const size_t span = meta[job.n - 1].text_offset + meta[job.n - 1].text_len + 1 - meta[0].pattern_offset;
+    size_t chunk = 0, n_chunks_unused = 0;
+    wfagpu_plan_chunks(job.n, opt.batch_size, ndev, span, &chunk, &n_chunks_unused);
     job.chunk = chunk;
     job.n_chunks = (job.n + chunk - 1) / chunk;
     pthread_mutex_init(&job.mu, NULL);

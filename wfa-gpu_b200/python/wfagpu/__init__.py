@@ -87,7 +87,8 @@ EXPORTS = [
     "wfagpu_device_align", "wfagpu_device_download", "wfagpu_device_last_stats", "wfagpu_device_sm_count",
     "wfagpu_device_pack_only", "wfagpu_ops_to_cigar", "wfagpu_set_devices", "wfagpu_last_run_stats",
     "wfagpu_synth_add_pairs", "wfagpu_device_wait", "wfagpu_host_register", "wfagpu_host_unregister",
-    "wfagpu_pairs_from_metadata", "wfagpu_reset_results",
+    "wfagpu_pairs_from_metadata", "wfagpu_reset_results", "wfagpu_read_seq_file", "wfagpu_read_fasta_files",
+    "wfagpu_check_result", "wfagpu_last_launch_ok", "wfagpu_plan_chunks",
 ]
 
 _lib = None
@@ -117,6 +118,14 @@ def load():
     L.wfagpu_destroy_aligner.argtypes = [P(AlignerStruct)]
     L.wfagpu_destroy_aligner.restype = None
     L.wfagpu_set_devices.argtypes = [C.c_char_p]
+    L.wfagpu_read_seq_file.argtypes = [P(AlignerStruct), C.c_char_p, C.c_size_t]
+    L.wfagpu_read_seq_file.restype = C.c_long
+    L.wfagpu_read_fasta_files.argtypes = [P(AlignerStruct), C.c_char_p, C.c_char_p, C.c_size_t]
+    L.wfagpu_read_fasta_files.restype = C.c_long
+    L.wfagpu_check_result.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, AffinePenalties, C.c_uint, C.c_char_p]
+    L.wfagpu_check_result.restype = C.c_bool
+    L.wfagpu_plan_chunks.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, P(C.c_size_t), P(C.c_size_t)]
+    L.wfagpu_plan_chunks.restype = None
     L.wfagpu_reset_results.argtypes = [P(AlignerStruct)]
     L.wfagpu_reset_results.restype = None
     L.wfagpu_last_run_stats.argtypes = [P(RunStats)]
@@ -221,6 +230,12 @@ class Aligner:
         p = C.string_at(base + m.pattern_offset, m.pattern_len)
         t = C.string_at(base + m.text_offset, m.text_len)
         return p.decode(), t.decode()
+
+    def read_seq_file(self, path, max_pairs=0):
+        return self.L.wfagpu_read_seq_file(C.byref(self.s), _b(path), max_pairs)
+
+    def read_fasta_files(self, query_path, target_path, max_pairs=0):
+        return self.L.wfagpu_read_fasta_files(C.byref(self.s), _b(query_path), _b(target_path), max_pairs)
 
     def add_synthetic(self, seed, n, length, err_lo, err_hi=None):
         if err_hi is None:
