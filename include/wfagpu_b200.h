@@ -71,6 +71,12 @@ typedef struct {
 #define WFAGPU_ST_OVERBUDGET 2u /* needs a larger wavefront budget (re-dispatch) */
 #define WFAGPU_ST_NEEDS_ASCII 4u /* flagged by the packer: byte-compare kernel    */
 
+/* Where a pair's CIGAR text sits in the text pool returned by wfagpu_device_download_text. */
+typedef struct {
+    uint32_t off; /* byte offset in the text pool */
+    uint32_t len; /* characters (no terminator); 0 = none */
+} wfagpu_cigar_ref_t;
+
 typedef struct wfagpu_device wfagpu_device_t; /* opaque: streams, buffers, arenas of one GPU */
 
 typedef struct {
@@ -121,6 +127,11 @@ int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wfagpu_pair_o
 /* Waits for the slot's stream; event-timed durations of the last pack and first
  * alignment launch (milliseconds). */
 int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, float *ms_align);
+/* After wfagpu_device_download: CIGAR text emitted on the device (one thread per pair, the
+ * reference's exact format) and compacted; `*text` / `*refs` point into pinned memory owned by
+ * the slot.  Replaces the host loop over recover_cigar_affine (utils/wfa_cpu.c:88-107). */
+int wfagpu_device_download_text(wfagpu_device_t *d, int slot, size_t n, const char **text, size_t *text_bytes,
+                                const wfagpu_cigar_ref_t **refs);
 void wfagpu_device_last_stats(wfagpu_device_t *d, int slot, wfagpu_batch_stats_t *st);
 /* Page-locks a caller buffer (e.g. the aligner's sequence buffer) so that the
  * H2D copies run as asynchronous DMA. */
@@ -148,6 +159,9 @@ int wfagpu_device_pack_only(wfagpu_device_t *d, const char *ascii, size_t ascii_
  * from the reference's backtrace chain.  Appends to `cigar`. */
 bool wfagpu_ops_to_cigar(const char *pattern, size_t plen, const char *text, size_t tlen,
                          int distance, const uint32_t *ops, uint32_t n_ops, wfa_cigar_t *cigar);
+
+/* Appends formatted CIGAR text to a result buffer (growing it like insert_ops does). */
+bool wfagpu_cigar_append(wfa_cigar_t *cigar, const char *text, size_t len);
 
 /* Device selection for launch_alignments*: "0", "0,1,2", "all", or a count
  * ("n:4").  Default (NULL/unset): environment WFAGPU_DEVICES, else device 0. */

@@ -109,6 +109,12 @@ struct Slot {
     DevBuf<uint32_t> scratch;
     DevBuf<int32_t> band_lo;
     DevBuf<int32_t> gring;
+    DevBuf<char> slots, text;
+    DevBuf<wfagpu_cigar_ref_t> refs;
+    DevBuf<unsigned long long> heads;
+    PinBuf<char> h_text;
+    PinBuf<wfagpu_cigar_ref_t> h_refs;
+    PinBuf<unsigned long long> h_heads;
     DevBuf<wfagpu_step_t> steps;
     PinBuf<wfagpu_pair_t> h_pairs;
     PinBuf<uint32_t> h_order;
@@ -210,7 +216,8 @@ extern "C" void wfagpu_device_close_all(void)
             s.ascii.release(); s.packed.release(); s.pairs.release(); s.order.release();
             s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
             s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release();
-            s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release();
+            s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release(); s.slots.release(); s.text.release(); s.refs.release(); s.heads.release();
+            s.h_text.release(); s.h_refs.release(); s.h_heads.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
             s.h_counters.release(); s.h_cells.release(); s.h_steps.release();
             for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -707,6 +714,56 @@ extern "C" int wfagpu_host_register(void *ptr, size_t bytes)
 extern "C" int wfagpu_host_unregister(void *ptr)
 {
     return cudaHostUnregister(ptr) == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int wfagpu_device_download_text(wfagpu_device_t *d, int slot, size_t n, const char **text, size_t *text_bytes,
+                                           const wfagpu_cigar_ref_t **refs)
+{
+    if (!d || slot < 0 || slot > 1 || !text || !text_bytes || !refs) return -1;
+    CK(cudaSetDevice(d->dev));
+    Slot &s = d->slots[slot];
+    if (n != s.n) return -1;
+    *text = nullptr; *text_bytes = 0; *refs = nullptr;
+    if (n == 0) return 0;
+    /* bound of the slack slots from the op pool: <= 16 ops per pool word, 10 chars per op (+ 32 per pair) */
+    const size_t pool_words = s.h_counters.p[CTR_POOL];
+    const size_t slot_bytes = 160 * pool_words + 40 * n + 64;
+    if (s.slots.ensure(slot_bytes) || s.text.ensure(slot_bytes) || s.refs.ensure(n) || s.heads.ensure(4) ||
+        s.h_refs.ensure(n) || s.h_heads.ensure(4))
+        return -1;
+    CK(cudaMemsetAsync(s.heads.p, 0, 4 * sizeof(unsigned long long), s.stream));
+    CigarParams cp{};
+    cp.ascii = s.ascii.p;
+    cp.pairs = s.pairs.p;
+    cp.out = s.out.p;
+    cp.ops_pool = s.pool.p;
+    cp.n_pairs = (uint32_t)n;
+    cp.slots = s.slots.p;
+    cp.slot_bytes = slot_bytes;
+    cp.slot_head = s.heads.p;
+    cp.text = s.text.p;
+    cp.text_head = s.heads.p + 1;
+    cp.refs = s.refs.p;
+    cp.overflow = reinterpret_cast<uint32_t *>(s.heads.p + 2);
+    launch_cigar_text(cp, s.stream);
+    CK(cudaGetLastError());
+    s.stats.launches += 2;
+    CK(cudaMemcpyAsync(s.h_heads.p, s.heads.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.h_refs.p, s.refs.p, n * sizeof(wfagpu_cigar_ref_t), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (s.h_heads.p[2] != 0) {
+        fprintf(stderr, "[wfagpu] CIGAR text pool overflow\n");
+        return -1;
+    }
+    const size_t used = (size_t)s.h_heads.p[1];
+    if (s.h_text.ensure(used + 1)) return -1;
+    if (used) CK(cudaMemcpyAsync(s.h_text.p, s.text.p, used, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    s.stats.d2h_bytes += used + n * sizeof(wfagpu_cigar_ref_t);
+    *text = s.h_text.p;
+    *text_bytes = used;
+    *refs = s.h_refs.p;
+    return 0;
 }
 
 extern "C" void wfagpu_device_last_stats(wfagpu_device_t *d, int slot, wfagpu_batch_stats_t *st)

@@ -965,6 +965,113 @@ int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii, bool bt)
     return bt ? occupancy_banded_one<false, true>(threads, smem_bytes) : occupancy_banded_one<false, false>(threads, smem_bytes);
 }
 
+/* ======================================================================== */
+/*                       CIGAR text emission on the device                  */
+/* ======================================================================== */
+/*
+ * Replaces the host stage recover_cigar_affine + insert_ops (utils/cigar.c:31-61,
+ * 96-272; OpenMP loop of utils/wfa_cpu.c:88-107): one thread per pair walks its
+ * op stream oldest first, re-derives the match runs on the ASCII copy that is
+ * already in HBM, and prints the run-length text ("%d%c", no '=') into a slot of
+ * the text pool.  Byte-for-byte the reference's output: X inside a gap is the
+ * gap-close delimiter and prints nothing, equal ops merge unless a delimiter or a
+ * match run separates them, score 0 prints "<tlen>M".  A second kernel compacts
+ * the slots so that only the text itself crosses PCIe.
+ */
+__device__ __forceinline__ uint32_t put_run(char *dst, uint32_t pos, uint32_t rep, char op)
+{
+    if (rep == 0) return pos;
+    char tmp[10];
+    int nd = 0;
+    while (rep) { tmp[nd++] = (char)('0' + rep % 10u); rep /= 10u; }
+    while (nd) dst[pos++] = tmp[--nd];
+    dst[pos++] = op;
+    return pos;
+}
+
+__device__ __forceinline__ uint32_t match_run_dev(const char *__restrict__ P, const char *__restrict__ T,
+                                                  int plen, int tlen, int v, int h)
+{
+    if (v < 0 || h < 0) return 0;
+    const int room = min(plen - v, tlen - h);
+    int n = 0;
+    while (n < room && P[v + n] == T[h + n]) ++n;
+    return (uint32_t)n;
+}
+
+__global__ void __launch_bounds__(128) cigar_text_kernel(CigarParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_pairs) return;
+    const wfagpu_pair_out_t o = p.out[i];
+    wfagpu_cigar_ref_t ref = {0u, 0u};
+    if (!(o.status & WFAGPU_ST_FINISHED)) { p.refs[i] = ref; return; }
+    const wfagpu_pair_t pr = p.pairs[i];
+    const char *P = p.ascii + pr.p_ascii, *T = p.ascii + pr.t_ascii;
+    const int plen = (int)pr.plen, tlen = (int)pr.tlen;
+    /* every op prints at most "1X" + "NNNNNNNM": 10 characters; plus the leading/trailing run */
+    const uint32_t cap = (10u * o.n_ops + 24u + 7u) & ~7u;
+    const unsigned long long slot = atomicAdd(p.slot_head, (unsigned long long)cap);
+    if (slot + cap > p.slot_bytes) { p.refs[i] = ref; atomicOr(p.overflow, 1u); return; }
+    char *dst = p.slots + slot;
+    uint32_t pos = 0;
+    if (o.distance == 0) {
+        pos = put_run(dst, pos, (uint32_t)tlen, 'M');
+    } else {
+        const uint32_t *ops = p.ops_pool + o.ops_off;
+        int k = 0, off = 0;
+        bool in_gap = false;
+        uint32_t run_op = OP_NOOP, run_len = 0;
+        for (uint32_t j = o.n_ops; j-- > 0;) {
+            uint32_t op = (ops[j >> 4] >> (2u * (j & 15u))) & 3u;
+            if (op != run_op && run_len) { pos = put_run(dst, pos, run_len, "?IXD"[run_op]); run_len = 0; }
+            if (!in_gap) {
+                const uint32_t m = match_run_dev(P, T, plen, tlen, off - k, off);
+                if (m) {
+                    if (run_len) { pos = put_run(dst, pos, run_len, "?IXD"[run_op]); run_len = 0; }
+                    pos = put_run(dst, pos, m, 'M');
+                    off += (int)m;
+                }
+            }
+            if (op == OP_DEL) { in_gap = true; --k; ++run_len; }
+            else if (op == OP_INS) { in_gap = true; ++k; ++off; ++run_len; }
+            else if (op == OP_SUB) {
+                if (in_gap) { in_gap = false; op = OP_NOOP; }
+                else { ++off; ++run_len; }
+            }
+            run_op = op;
+        }
+        if (run_len) pos = put_run(dst, pos, run_len, "?IXD"[run_op]);
+        if (!in_gap) pos = put_run(dst, pos, match_run_dev(P, T, plen, tlen, off - k, off), 'M');
+    }
+    ref.off = (uint32_t)(slot >> 3);          /* slots are 8-byte aligned */
+    ref.len = pos;
+    p.refs[i] = ref;
+}
+
+/* One warp per pair: move the text from its slack slot to a dense pool. */
+__global__ void __launch_bounds__(256) cigar_compact_kernel(CigarParams p)
+{
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= p.n_pairs) return;
+    wfagpu_cigar_ref_t ref = p.refs[i];
+    if (ref.len == 0) return;
+    uint32_t dst_off = 0;
+    if (lane == 0) dst_off = (uint32_t)atomicAdd(p.text_head, (unsigned long long)ref.len);
+    dst_off = __shfl_sync(0xffffffffu, dst_off, 0);
+    const char *src = p.slots + ((unsigned long long)ref.off << 3);
+    for (uint32_t j = lane; j < ref.len; j += 32) p.text[dst_off + j] = src[j];
+    if (lane == 0) { ref.off = dst_off; p.refs[i] = ref; }
+}
+
+void launch_cigar_text(const CigarParams &p, cudaStream_t s)
+{
+    if (p.n_pairs == 0) return;
+    cigar_text_kernel<<<(p.n_pairs + 127) / 128, 128, 0, s>>>(p);
+    cigar_compact_kernel<<<(p.n_pairs + 7) / 8, 256, 0, s>>>(p);
+}
+
 /* ---- host-side launch helpers ---------------------------------------------- */
 
 template <bool WARP, bool ASCII, bool BT, typename R = RingS16>

@@ -77,7 +77,23 @@ struct PackParams {
     uint32_t n_pairs;
 };
 
+struct CigarParams {
+    const char *ascii;
+    const wfagpu_pair_t *pairs;
+    const wfagpu_pair_out_t *out;
+    const uint32_t *ops_pool;
+    uint32_t n_pairs;
+    char *slots;                      /* slack slots, bump-allocated in 8-byte units            */
+    unsigned long long slot_bytes;
+    unsigned long long *slot_head;
+    char *text;                       /* dense text pool                                        */
+    unsigned long long *text_head;
+    wfagpu_cigar_ref_t *refs;         /* per pair: offset (bytes) + length of its text          */
+    uint32_t *overflow;
+};
+
 void launch_pack(const PackParams &p, cudaStream_t s);
+void launch_cigar_text(const CigarParams &p, cudaStream_t s);
 /* group_threads == 32 -> warp-per-pair variant; otherwise CTA-per-pair */
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
                          size_t smem_bytes, bool ascii_extend, cudaStream_t s);

@@ -75,6 +75,7 @@ typedef struct {
     size_t next_chunk;      /* guarded by mu */
     pthread_mutex_t mu;
     bool failed;
+    bool host_cigar;        /* WFAGPU_HOST_CIGAR=1: print the CIGAR text on the host instead of the GPU */
     int decode_threads;
     /* accumulated stats */
     wfagpu_run_stats_t stats;
@@ -201,10 +202,18 @@ static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu
     wfagpu_device_last_stats(d, slot, &bs);
     acc->gpu_align_ms += bs.ms_align;
     acc->gpu_pack_ms += bs.ms_pack;
-    acc->launches += bs.launches;
     acc->redispatched += bs.redispatched;
     acc->ascii_pairs += bs.ascii_pairs;
     acc->h2d_bytes += bs.h2d_bytes;
+
+    const char *text = NULL;
+    size_t text_bytes = 0;
+    const wfagpu_cigar_ref_t *refs = NULL;
+    if (j->cigar && !j->host_cigar) {
+        if (wfagpu_device_download_text(d, slot, f->n, &text, &text_bytes, &refs)) return -1;
+        wfagpu_device_last_stats(d, slot, &bs);
+    }
+    acc->launches += bs.launches;
     acc->d2h_bytes += bs.d2h_bytes;
 
     const sequence_pair_t *m = j->meta + f->from;
@@ -216,7 +225,10 @@ static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu
         const wfagpu_pair_out_t *o = &f->out[i];
         if (!(o->status & WFAGPU_ST_FINISHED)) { bad++; continue; }
         res[i].error = (unsigned int)o->distance;
-        if (j->cigar) {
+        if (j->cigar && refs) {
+            /* text was printed on the GPU: append it to the caller's buffer */
+            if (!wfagpu_cigar_append(&res[i].cigar, text + refs[i].off, refs[i].len)) bad++;
+        } else if (j->cigar) {
             if (!wfagpu_ops_to_cigar(j->buf + m[i].pattern_offset, m[i].pattern_len, j->buf + m[i].text_offset,
                                      m[i].text_len, o->distance, ops + o->ops_off, o->n_ops, &res[i].cigar))
                 bad++;
@@ -327,7 +339,11 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     job.n_chunks = (job.n + chunk - 1) / chunk;
     pthread_mutex_init(&job.mu, NULL);
     int cores = omp_get_num_procs();
+    const char *ht = getenv("WFAGPU_HOST_THREADS");
+    if (ht && atoi(ht) > 0) cores = atoi(ht);
     job.decode_threads = cores / ndev > 0 ? cores / ndev : 1;
+    const char *hc = getenv("WFAGPU_HOST_CIGAR");
+    job.host_cigar = hc && atoi(hc) != 0;
 
     const int nworkers = (size_t)ndev < job.n_chunks ? ndev : (int)job.n_chunks;
     worker_t workers[MAX_DEVICES];

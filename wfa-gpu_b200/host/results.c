@@ -3,7 +3,7 @@
  * (replaces lib/alignment_results.c:24-54 and insert_ops, utils/cigar.c:31-61).
  */
 #include <string.h>
-#include "wfa_gpu.h"
+#include "wfagpu_b200.h"
 
 bool initialize_wfa_results(wfa_alignment_result_t **results, const size_t num_alignments,
                             const size_t cigar_length)
@@ -58,5 +58,16 @@ bool insert_ops(wfa_cigar_t *const cigar, const char op, const unsigned int rep)
     *w++ = op;
     *w = 0;
     cigar->last_free_position += (size_t)nd + 1;
+    return true;
+}
+
+/* Appends `len` characters of already formatted CIGAR text (printed on the GPU). */
+bool wfagpu_cigar_append(wfa_cigar_t *cigar, const char *text, size_t len)
+{
+    if (len == 0) return true;
+    if (!cigar_reserve(cigar, len)) return false;
+    memcpy(cigar->buffer + cigar->last_free_position, text, len);
+    cigar->last_free_position += len;
+    cigar->buffer[cigar->last_free_position] = 0;
     return true;
 }
