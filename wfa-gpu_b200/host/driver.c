@@ -75,6 +75,7 @@ typedef struct {
     size_t next_chunk;      /* guarded by mu */
     pthread_mutex_t mu;
     bool failed;
+    bool verbose;
     bool host_cigar;        /* WFAGPU_HOST_CIGAR=1: print the CIGAR text on the host instead of the GPU */
     int decode_threads;
     /* accumulated stats */
@@ -94,6 +95,13 @@ typedef struct {
     wfagpu_pair_out_t *out;
     size_t out_cap;
 } inflight_t;
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static bool take_chunk(job_t *j, size_t *from, size_t *n)
 {
@@ -196,7 +204,9 @@ static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu
 {
     uint32_t *ops = NULL;
     size_t ops_used = 0;
+    const double t_a = now_s();
     if (wfagpu_device_download(d, slot, f->n, f->out, &ops, &ops_used, NULL)) return -1;
+    const double t_b = now_s();
     f->active = false;
     wfagpu_batch_stats_t bs;
     wfagpu_device_last_stats(d, slot, &bs);
@@ -215,6 +225,7 @@ static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu
     }
     acc->launches += bs.launches;
     acc->d2h_bytes += bs.d2h_bytes;
+    const double t_c = now_s();
 
     const sequence_pair_t *m = j->meta + f->from;
     wfa_alignment_result_t *res = j->res + f->from;
@@ -238,6 +249,9 @@ static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu
         fprintf(stderr, "[!] ERROR: %d alignments of the batch starting at %zu were not completed on the GPU.\n", bad, f->from);
         return -1;
     }
+    if (j->verbose)
+        fprintf(stderr, "[wfagpu] chunk from=%zu n=%zu: wait+download %.2f ms, text %.2f ms, host results %.2f ms (kernel %.2f ms)\n",
+                f->from, f->n, (t_b - t_a) * 1e3, (t_c - t_b) * 1e3, (now_s() - t_c) * 1e3, bs.ms_align);
     return 0;
 }
 
@@ -281,13 +295,6 @@ static void *worker_main(void *arg)
     j->stats.d2h_bytes += acc.d2h_bytes;
     pthread_mutex_unlock(&j->mu);
     return NULL;
-}
-
-static double now_s(void)
-{
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
 /* How the pair range is cut: chunks of at most `batch_size` pairs; with several GPUs at
@@ -342,6 +349,8 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     const char *ht = getenv("WFAGPU_HOST_THREADS");
     if (ht && atoi(ht) > 0) cores = atoi(ht);
     job.decode_threads = cores / ndev > 0 ? cores / ndev : 1;
+    const char *vb = getenv("WFAGPU_VERBOSE");
+    job.verbose = vb && atoi(vb) != 0;
     const char *hc = getenv("WFAGPU_HOST_CIGAR");
     job.host_cigar = hc && atoi(hc) != 0;
 
