@@ -133,6 +133,8 @@ struct Slot {
     wfagpu_plan_t plan{};
     wfagpu_batch_stats_t stats{};
     bool have_events = false;
+    bool text_queued = false; /* cigar_text kernels already follow the last alignment pass */
+    int last_d_end = 0;
     bool capped = false;      /* the first pass provisioned fewer diagonals than the budget allows */
 };
 
@@ -149,6 +151,7 @@ struct wfagpu_device {
     int hint_key[3] = {-1, -1, -1};
     bool use_hint = true;
     bool force_large = false;
+    bool device_text = true;   /* WFAGPU_HOST_CIGAR=1 leaves the text to the host */
 };
 
 static std::mutex g_mu;
@@ -202,6 +205,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->force_warp = env_int("WFAGPU_WARP_KERNEL", -1);
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
     d->force_large = env_int("WFAGPU_FORCE_LARGE", 0) != 0;
+    d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;
     g_devices.push_back(d);
     return d;
 }
@@ -559,6 +563,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         return -1;
     }
     s.stats.launches += 1;
+    s.last_d_end = std::max(s.last_d_end, d_end);
+    s.text_queued = false;
     return 0;
 }
 
@@ -583,9 +589,12 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
     CK(cudaGetLastError());
     s.stats.launches += 1;
     CK(cudaEventRecord(s.ev[3], s.stream));
+    s.last_d_end = 0;
     int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, true, true, &s.capped);
     if (rc) return rc;
     CK(cudaEventRecord(s.ev[4], s.stream));
+    d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;   /* re-read: tests flip it between runs */
+    if (plan->with_cigar && d->device_text && enqueue_text(d, s, n, s.last_d_end)) return -1;
     return 0;
 }
 
@@ -716,18 +725,13 @@ extern "C" int wfagpu_host_unregister(void *ptr)
     return cudaHostUnregister(ptr) == cudaSuccess ? 0 : -1;
 }
 
-extern "C" int wfagpu_device_download_text(wfagpu_device_t *d, int slot, size_t n, const char **text, size_t *text_bytes,
-                                           const wfagpu_cigar_ref_t **refs)
+/* CIGAR text on the device: queued right behind the alignment kernel so that it overlaps with
+ * the host's work on the previous chunk; redone by download() if pairs had to be re-dispatched. */
+static int enqueue_text(wfagpu_device *d, Slot &s, size_t n, int d_end_bound)
 {
-    if (!d || slot < 0 || slot > 1 || !text || !text_bytes || !refs) return -1;
-    CK(cudaSetDevice(d->dev));
-    Slot &s = d->slots[slot];
-    if (n != s.n) return -1;
-    *text = nullptr; *text_bytes = 0; *refs = nullptr;
-    if (n == 0) return 0;
-    /* bound of the slack slots from the op pool: <= 16 ops per pool word, 10 chars per op (+ 32 per pair) */
-    const size_t pool_words = s.h_counters.p[CTR_POOL];
-    const size_t slot_bytes = 160 * pool_words + 40 * n + 64;
+    (void)d;
+    /* slack slots: 10 characters per op, at most 2 ops per score */
+    const size_t slot_bytes = n * ((size_t)20 * (size_t)d_end_bound + 64) + 64;
     if (s.slots.ensure(slot_bytes) || s.text.ensure(slot_bytes) || s.refs.ensure(n) || s.heads.ensure(4) ||
         s.h_refs.ensure(n) || s.h_heads.ensure(4))
         return -1;
@@ -750,6 +754,20 @@ extern "C" int wfagpu_device_download_text(wfagpu_device_t *d, int slot, size_t 
     s.stats.launches += 2;
     CK(cudaMemcpyAsync(s.h_heads.p, s.heads.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaMemcpyAsync(s.h_refs.p, s.refs.p, n * sizeof(wfagpu_cigar_ref_t), cudaMemcpyDeviceToHost, s.stream));
+    s.text_queued = true;
+    return 0;
+}
+
+extern "C" int wfagpu_device_download_text(wfagpu_device_t *d, int slot, size_t n, const char **text, size_t *text_bytes,
+                                           const wfagpu_cigar_ref_t **refs)
+{
+    if (!d || slot < 0 || slot > 1 || !text || !text_bytes || !refs) return -1;
+    CK(cudaSetDevice(d->dev));
+    Slot &s = d->slots[slot];
+    if (n != s.n) return -1;
+    *text = nullptr; *text_bytes = 0; *refs = nullptr;
+    if (n == 0) return 0;
+    if (!s.text_queued && enqueue_text(d, s, n, s.last_d_end)) return -1;
     CK(cudaStreamSynchronize(s.stream));
     if (s.h_heads.p[2] != 0) {
         fprintf(stderr, "[wfagpu] CIGAR text pool overflow\n");

@@ -980,56 +980,73 @@ int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii, bool bt)
  */
 __device__ __forceinline__ uint32_t put_run(char *dst, uint32_t pos, uint32_t rep, char op)
 {
+    /* "%d%c" (insert_ops, utils/cigar.c:31-61); nothing for an empty run */
     if (rep == 0) return pos;
-    char tmp[10];
-    int nd = 0;
-    while (rep) { tmp[nd++] = (char)('0' + rep % 10u); rep /= 10u; }
-    while (nd) dst[pos++] = tmp[--nd];
+    uint32_t div = 1;
+    while (rep / div >= 10u) div *= 10u;
+    for (; div; div /= 10u) dst[pos++] = (char)('0' + (rep / div) % 10u);
     dst[pos++] = op;
     return pos;
 }
 
-__device__ __forceinline__ uint32_t match_run_dev(const char *__restrict__ P, const char *__restrict__ T,
-                                                  int plen, int tlen, int v, int h)
+/* Match run from (v, h), found by the whole warp: 32 bases per round, ballot + ffs. */
+__device__ __forceinline__ uint32_t match_run_warp(const char *__restrict__ P, const char *__restrict__ T,
+                                                   int plen, int tlen, int v, int h, int lane)
 {
     if (v < 0 || h < 0) return 0;
     const int room = min(plen - v, tlen - h);
     int n = 0;
-    while (n < room && P[v + n] == T[h + n]) ++n;
-    return (uint32_t)n;
+    while (n < room) {
+        const int j = n + lane;
+        const bool diff = (j >= room) || (P[v + j] != T[h + j]);
+        const uint32_t m = __ballot_sync(0xffffffffu, diff);
+        if (m) return (uint32_t)(n + (__ffs((int)m) - 1));
+        n += 32;
+    }
+    return (uint32_t)room;
 }
 
-__global__ void __launch_bounds__(128) cigar_text_kernel(CigarParams p)
+/* One warp per pair.  The op walk is sequential; the warp shares the match-run scans
+ * (coalesced 32-byte reads of both sequences) and lane 0 prints. */
+__global__ void __launch_bounds__(256) cigar_text_kernel(CigarParams p)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (i >= p.n_pairs) return;
     const wfagpu_pair_out_t o = p.out[i];
     wfagpu_cigar_ref_t ref = {0u, 0u};
-    if (!(o.status & WFAGPU_ST_FINISHED)) { p.refs[i] = ref; return; }
+    if (!(o.status & WFAGPU_ST_FINISHED)) { if (lane == 0) p.refs[i] = ref; return; }
     const wfagpu_pair_t pr = p.pairs[i];
     const char *P = p.ascii + pr.p_ascii, *T = p.ascii + pr.t_ascii;
     const int plen = (int)pr.plen, tlen = (int)pr.tlen;
     /* every op prints at most "1X" + "NNNNNNNM": 10 characters; plus the leading/trailing run */
     const uint32_t cap = (10u * o.n_ops + 24u + 7u) & ~7u;
-    const unsigned long long slot = atomicAdd(p.slot_head, (unsigned long long)cap);
-    if (slot + cap > p.slot_bytes) { p.refs[i] = ref; atomicOr(p.overflow, 1u); return; }
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(p.slot_head, (unsigned long long)cap);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot + cap > p.slot_bytes) {
+        if (lane == 0) { p.refs[i] = ref; atomicOr(p.overflow, 1u); }
+        return;
+    }
     char *dst = p.slots + slot;
-    uint32_t pos = 0;
+    uint32_t pos = 0;                                   /* meaningful in lane 0 only */
     if (o.distance == 0) {
-        pos = put_run(dst, pos, (uint32_t)tlen, 'M');
+        if (lane == 0) pos = put_run(dst, pos, (uint32_t)tlen, 'M');
     } else {
         const uint32_t *ops = p.ops_pool + o.ops_off;
         int k = 0, off = 0;
         bool in_gap = false;
         uint32_t run_op = OP_NOOP, run_len = 0;
+        uint32_t word = 0;
         for (uint32_t j = o.n_ops; j-- > 0;) {
-            uint32_t op = (ops[j >> 4] >> (2u * (j & 15u))) & 3u;
-            if (op != run_op && run_len) { pos = put_run(dst, pos, run_len, "?IXD"[run_op]); run_len = 0; }
+            if ((j & 15u) == 15u || j == o.n_ops - 1) word = ops[j >> 4];
+            uint32_t op = (word >> (2u * (j & 15u))) & 3u;
+            if (op != run_op && run_len) { if (lane == 0) pos = put_run(dst, pos, run_len, "?IXD"[run_op]); run_len = 0; }
             if (!in_gap) {
-                const uint32_t m = match_run_dev(P, T, plen, tlen, off - k, off);
+                const uint32_t m = match_run_warp(P, T, plen, tlen, off - k, off, lane);
                 if (m) {
-                    if (run_len) { pos = put_run(dst, pos, run_len, "?IXD"[run_op]); run_len = 0; }
-                    pos = put_run(dst, pos, m, 'M');
+                    if (run_len) { if (lane == 0) pos = put_run(dst, pos, run_len, "?IXD"[run_op]); run_len = 0; }
+                    if (lane == 0) pos = put_run(dst, pos, m, 'M');
                     off += (int)m;
                 }
             }
@@ -1041,12 +1058,17 @@ __global__ void __launch_bounds__(128) cigar_text_kernel(CigarParams p)
             }
             run_op = op;
         }
-        if (run_len) pos = put_run(dst, pos, run_len, "?IXD"[run_op]);
-        if (!in_gap) pos = put_run(dst, pos, match_run_dev(P, T, plen, tlen, off - k, off), 'M');
+        if (run_len && lane == 0) pos = put_run(dst, pos, run_len, "?IXD"[run_op]);
+        if (!in_gap) {
+            const uint32_t m = match_run_warp(P, T, plen, tlen, off - k, off, lane);
+            if (lane == 0) pos = put_run(dst, pos, m, 'M');
+        }
     }
-    ref.off = (uint32_t)(slot >> 3);          /* slots are 8-byte aligned */
-    ref.len = pos;
-    p.refs[i] = ref;
+    if (lane == 0) {
+        ref.off = (uint32_t)(slot >> 3);          /* slots are 8-byte aligned */
+        ref.len = pos;
+        p.refs[i] = ref;
+    }
 }
 
 /* One warp per pair: move the text from its slack slot to a dense pool. */
@@ -1068,7 +1090,7 @@ __global__ void __launch_bounds__(256) cigar_compact_kernel(CigarParams p)
 void launch_cigar_text(const CigarParams &p, cudaStream_t s)
 {
     if (p.n_pairs == 0) return;
-    cigar_text_kernel<<<(p.n_pairs + 127) / 128, 128, 0, s>>>(p);
+    cigar_text_kernel<<<(p.n_pairs + 7) / 8, 256, 0, s>>>(p);
     cigar_compact_kernel<<<(p.n_pairs + 7) / 8, 256, 0, s>>>(p);
 }
 
