@@ -568,6 +568,39 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     return 0;
 }
 
+/* CIGAR text on the device: queued right behind the alignment kernel so that it overlaps with
+ * the host's work on the previous chunk; redone by download() if pairs had to be re-dispatched. */
+static int enqueue_text(wfagpu_device *d, Slot &s, size_t n, int d_end_bound)
+{
+    (void)d;
+    /* slack slots: 10 characters per op, at most 2 ops per score */
+    const size_t slot_bytes = n * ((size_t)20 * (size_t)d_end_bound + 64) + 64;
+    if (s.slots.ensure(slot_bytes) || s.text.ensure(slot_bytes) || s.refs.ensure(n) || s.heads.ensure(4) ||
+        s.h_refs.ensure(n) || s.h_heads.ensure(4))
+        return -1;
+    CK(cudaMemsetAsync(s.heads.p, 0, 4 * sizeof(unsigned long long), s.stream));
+    CigarParams cp{};
+    cp.ascii = s.ascii.p;
+    cp.pairs = s.pairs.p;
+    cp.out = s.out.p;
+    cp.ops_pool = s.pool.p;
+    cp.n_pairs = (uint32_t)n;
+    cp.slots = s.slots.p;
+    cp.slot_bytes = slot_bytes;
+    cp.slot_head = s.heads.p;
+    cp.text = s.text.p;
+    cp.text_head = s.heads.p + 1;
+    cp.refs = s.refs.p;
+    cp.overflow = reinterpret_cast<uint32_t *>(s.heads.p + 2);
+    launch_cigar_text(cp, s.stream);
+    CK(cudaGetLastError());
+    s.stats.launches += 2;
+    CK(cudaMemcpyAsync(s.h_heads.p, s.heads.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.h_refs.p, s.refs.p, n * sizeof(wfagpu_cigar_ref_t), cudaMemcpyDeviceToHost, s.stream));
+    s.text_queued = true;
+    return 0;
+}
+
 extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const wfagpu_plan_t *plan, int resident)
 {
     (void)resident;
@@ -723,39 +756,6 @@ extern "C" int wfagpu_host_register(void *ptr, size_t bytes)
 extern "C" int wfagpu_host_unregister(void *ptr)
 {
     return cudaHostUnregister(ptr) == cudaSuccess ? 0 : -1;
-}
-
-/* CIGAR text on the device: queued right behind the alignment kernel so that it overlaps with
- * the host's work on the previous chunk; redone by download() if pairs had to be re-dispatched. */
-static int enqueue_text(wfagpu_device *d, Slot &s, size_t n, int d_end_bound)
-{
-    (void)d;
-    /* slack slots: 10 characters per op, at most 2 ops per score */
-    const size_t slot_bytes = n * ((size_t)20 * (size_t)d_end_bound + 64) + 64;
-    if (s.slots.ensure(slot_bytes) || s.text.ensure(slot_bytes) || s.refs.ensure(n) || s.heads.ensure(4) ||
-        s.h_refs.ensure(n) || s.h_heads.ensure(4))
-        return -1;
-    CK(cudaMemsetAsync(s.heads.p, 0, 4 * sizeof(unsigned long long), s.stream));
-    CigarParams cp{};
-    cp.ascii = s.ascii.p;
-    cp.pairs = s.pairs.p;
-    cp.out = s.out.p;
-    cp.ops_pool = s.pool.p;
-    cp.n_pairs = (uint32_t)n;
-    cp.slots = s.slots.p;
-    cp.slot_bytes = slot_bytes;
-    cp.slot_head = s.heads.p;
-    cp.text = s.text.p;
-    cp.text_head = s.heads.p + 1;
-    cp.refs = s.refs.p;
-    cp.overflow = reinterpret_cast<uint32_t *>(s.heads.p + 2);
-    launch_cigar_text(cp, s.stream);
-    CK(cudaGetLastError());
-    s.stats.launches += 2;
-    CK(cudaMemcpyAsync(s.h_heads.p, s.heads.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaMemcpyAsync(s.h_refs.p, s.refs.p, n * sizeof(wfagpu_cigar_ref_t), cudaMemcpyDeviceToHost, s.stream));
-    s.text_queued = true;
-    return 0;
 }
 
 extern "C" int wfagpu_device_download_text(wfagpu_device_t *d, int slot, size_t n, const char **text, size_t *text_bytes,
