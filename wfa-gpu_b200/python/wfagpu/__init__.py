@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libwfagpu.so"))
+LIB_PATH = os.environ.get("WFAGPU_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libwfagpu.so"))
 
 BAND_NONE = -1
 
