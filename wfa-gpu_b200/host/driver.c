@@ -345,7 +345,10 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     job.chunk = chunk;
     job.n_chunks = (job.n + chunk - 1) / chunk;
     pthread_mutex_init(&job.mu, NULL);
+    /* host threads per GPU worker for the result loop: respect OMP_NUM_THREADS (torchrun sets it to 1
+     * per rank) and never oversubscribe when several workers share the box */
     int cores = omp_get_num_procs();
+    if (omp_get_max_threads() < cores) cores = omp_get_max_threads();
     const char *ht = getenv("WFAGPU_HOST_THREADS");
     if (ht && atoi(ht) > 0) cores = atoi(ht);
     job.decode_threads = cores / ndev > 0 ? cores / ndev : 1;
@@ -353,6 +356,7 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     job.verbose = vb && atoi(vb) != 0;
     const char *hc = getenv("WFAGPU_HOST_CIGAR");
     job.host_cigar = hc && atoi(hc) != 0;
+    if (!job.host_cigar && job.decode_threads > 4) job.decode_threads = 4;   /* only memcpy of finished text is left */
 
     const int nworkers = (size_t)ndev < job.n_chunks ? ndev : (int)job.n_chunks;
     worker_t workers[MAX_DEVICES];
