@@ -263,7 +263,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(rs["h2d_bytes"]), "d2h_bytes_per_step": int(rs["d2h_bytes"]),
                 "gcups": round(gcells_total * world * args.steps / t_e2e_max / 1e9, 1),
-                "api": "wfagpu_align (page-locked host buffers, CIGAR text generated on the host)"},
+                "api": "wfagpu_align (page-locked host buffers; H2D, kernels, CIGAR text printed on the GPU, D2H, copy into results[i])"},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks, "roofline": roofline, "roofline_int": roofline_int,
     }
@@ -283,9 +283,9 @@ def cpu_baseline(a, sample):
     pairs = [a.pair(i) for i in range(n)]
     if RefCPU.available():
         r = RefCPU()
-        threads = r.max_threads()
+        threads = len(os.sched_getaffinity(0))          # all host cores (torchrun pins OMP_NUM_THREADS=1)
         t0 = time.perf_counter()
-        errs, _ = r.align_batch([p for p, _ in pairs], [t for _, t in pairs], *PEN, cigar=True)
+        errs, _ = r.align_batch([p for p, _ in pairs], [t for _, t in pairs], *PEN, cigar=True, threads=threads)
         dt = time.perf_counter() - t0
         for i in range(0, n, 37):
             assert errs[i] == a.error(i), "CPU reference and GPU scores differ"
@@ -316,8 +316,8 @@ def run_reference(args):
     P, T = [p for p, _ in pairs], [t for _, t in pairs]
     if RefCPU.available():
         r = RefCPU()
-        threads, kind = r.max_threads(), "reference"
-        step = lambda: r.align_batch(P, T, *PEN, cigar=True)
+        threads, kind = len(os.sched_getaffinity(0)), "reference"
+        step = lambda: r.align_batch(P, T, *PEN, cigar=True, threads=threads)
         n = len(P)
     else:
         o = Oracle()
