@@ -42,7 +42,7 @@ typedef struct {
  * steps >= max_steps-1 (sequence_alignment_kernel.cu:584, steps starts at 1).
  * banded_win == 0: exact kernels (n = computed half width, row_off = bit-plane row);
  * banded_win  > 0: banded kernels (n = number of M/I/D steps so far, rows of
- * ceil(win/32) units). */
+ * ceil(win/16) units).  A decision row holds one byte per diagonal. */
 int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist, int banded_win,
                             wfagpu_step_t *tab, uint64_t *arena_units);
 

@@ -12,7 +12,7 @@
  *   - "clean" source semantics (a source that does not exist reads as NULL;
  *     the reference reads stale ring contents instead, which can never lie on
  *     an optimal path -- see DESIGN.md "Why clean rings are exact"),
- *   - 4 decision bit-planes per 32 diagonals instead of piggy-backed 32-bit
+ *   - one decision byte per cell (I ext, D ext, M winner) instead of piggy-backed 32-bit
  *     words + prev pointers, followed by a geometric traceback that emits the
  *     same 2-bit op stream the reference's chain decodes to.
  *
@@ -30,7 +30,7 @@
 
 typedef struct {
     int32_t n;        /* half width of the range after this step            */
-    uint32_t row_off; /* decision row offset, in u32 words, MDI steps only  */
+    uint32_t row_off; /* decision row offset, in bytes, MDI steps only      */
     uint8_t kind;
 } km_step_t;
 
@@ -38,7 +38,7 @@ typedef struct {
  * wfa-gpu_b200/host/step_table.c.  Existence logic follows
  * lib/kernels/sequence_alignment_kernel.cu:584-631 (it depends on the
  * penalties only).  Returns d_end: scores 1 .. d_end-1 may be computed. */
-int km_build_steps(int x, int o, int e, int max_steps, int max_dist, km_step_t *tab, uint64_t *arena_words)
+int km_build_steps(int x, int o, int e, int max_steps, int max_dist, km_step_t *tab, uint64_t *arena_bytes)
 {
     uint8_t *exM = (uint8_t *)calloc((size_t)max_dist + 1, 1);
     uint8_t *exI = (uint8_t *)calloc((size_t)max_dist + 1, 1);
@@ -64,10 +64,10 @@ int km_build_steps(int x, int o, int e, int max_steps, int max_dist, km_step_t *
         }
         tab[d].n = n;
         tab[d].row_off = (uint32_t)off;
-        if (tab[d].kind == KM_KIND_MDI) off += 4u * (uint64_t)((2 * n + 1 + 31) / 32);
+        if (tab[d].kind == KM_KIND_MDI) off += 16u * (uint64_t)((2 * n + 1 + 15) / 16);
     }
     free(exM); free(exI);
-    if (arena_words) *arena_words = off;
+    if (arena_bytes) *arena_bytes = off;
     return d;
 }
 
@@ -100,10 +100,10 @@ int km_align_pair(const char *pattern, int plen, const char *text, int tlen,
     int16_t *Mr = (int16_t *)malloc((size_t)A * W * sizeof(int16_t));
     int16_t *Ir = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
     int16_t *Dr = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
-    uint64_t arena_words = 0;
+    uint64_t arena_bytes = 0;
     for (int d = 0; d < d_end; d++)
-        if (tab[d].kind == KM_KIND_MDI) arena_words = tab[d].row_off + 4u * (uint64_t)((2 * tab[d].n + 1 + 31) / 32);
-    uint32_t *arena = with_bt ? (uint32_t *)calloc(arena_words + 4, sizeof(uint32_t)) : NULL;
+        if (tab[d].kind == KM_KIND_MDI) arena_bytes = tab[d].row_off + 16u * (uint64_t)((2 * tab[d].n + 1 + 15) / 16);
+    uint8_t *arena = with_bt ? (uint8_t *)calloc(arena_bytes + 16, 1) : NULL;
     /* poison the rings: the kernel never clears them between pairs */
     for (long i = 0; i < (long)A * W; i++) Mr[i] = 12345;
     for (long i = 0; i < (long)E1 * W; i++) { Ir[i] = 12345; Dr[i] = 12345; }
@@ -147,7 +147,7 @@ int km_align_pair(const char *pattern, int plen, const char *text, int tlen,
                 const int16_t *Ie = Ir + ((((d - e) % E1) + E1) % E1) * W + C;
                 const int16_t *De = Dr + ((((d - e) % E1) + E1) % E1) * W + C;
                 const int16_t *Mxx = Mr + ((((d - x) % A) + A) % A) * W + C;
-                uint32_t *row = with_bt ? arena + st.row_off : NULL;
+                uint8_t *row = with_bt ? arena + st.row_off : NULL;
                 for (int k = -n - G; k < -n; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
                 for (int k = n + 1; k <= n + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
                 for (int k = -n; k <= n; k++) {
@@ -163,13 +163,7 @@ int km_align_pair(const char *pattern, int plen, const char *text, int tlen,
                     const int mop = pM & 3;
                     if (M >= 0) M = km_extend(text, pattern, tlen, plen, k, M);
                     Ic[k] = (int16_t)I; Dc[k] = (int16_t)D; Mc[k] = (int16_t)M;
-                    if (with_bt) {
-                        const int idx = k + n, g = idx >> 5, b = idx & 31;
-                        if (pI & 1)  row[4 * g + 0] |= 1u << b;
-                        if (pD & 1)  row[4 * g + 1] |= 1u << b;
-                        if (mop & 1) row[4 * g + 2] |= 1u << b;
-                        if (mop & 2) row[4 * g + 3] |= 1u << b;
-                    }
+                    if (with_bt) row[k + n] = (uint8_t)((pI & 1) | ((pD & 1) << 1) | (mop << 2));
                     cells++;
                 }
             }
@@ -191,23 +185,20 @@ int km_align_pair(const char *pattern, int plen, const char *text, int tlen,
             if (comp == 0) {
                 ops_out[cnt++] = 2;
                 if (st.kind == KM_KIND_M) { cd -= x; continue; }
-                const int idx = ck + st.n, g = idx >> 5, b = idx & 31;
-                const uint32_t *row = arena + st.row_off + 4 * g;
-                const int mop = (int)((row[2] >> b) & 1) | (int)(((row[3] >> b) & 1) << 1);
+                const int mop = (arena[st.row_off + ck + st.n] >> 2) & 3;
                 if (mop == 2) cd -= x;
                 else if (mop == 1) comp = 1;
                 else comp = 2;
             } else {
-                const int idx = ck + st.n, g = idx >> 5, b = idx & 31;
-                const uint32_t *row = arena + st.row_off + 4 * g;
+                const uint8_t dec = arena[st.row_off + ck + st.n];
                 if (comp == 1) {
                     ops_out[cnt++] = 1;
-                    const int ext = (int)((row[0] >> b) & 1);
+                    const int ext = dec & 1;
                     ck -= 1;
                     if (ext) cd -= e; else { cd -= o + e; comp = 0; }
                 } else {
                     ops_out[cnt++] = 3;
-                    const int ext = (int)((row[1] >> b) & 1);
+                    const int ext = (dec >> 1) & 1;
                     ck += 1;
                     if (ext) cd -= e; else { cd -= o + e; comp = 0; }
                 }

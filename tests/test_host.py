@@ -103,11 +103,11 @@ def test_step_table_equals_model(lib, oracle, pen):
     d1 = lib.wfagpu_build_step_table(x, o, e, ms, md, 0, t1, C.byref(u1))
     t2 = (KmStep * (md + 1))(); u2 = C.c_uint64()
     d2 = oracle.L.km_build_steps(x, o, e, ms, md, t2, C.byref(u2))
-    assert d1 == d2 and u1.value * 4 == u2.value
+    assert d1 == d2 and u1.value * 16 == u2.value
     for d in range(d1):
         assert (t1[d].kind, t1[d].n) == (t2[d].kind, t2[d].n)
         if t1[d].kind == 2:
-            assert t1[d].row_off * 4 == t2[d].row_off
+            assert t1[d].row_off * 16 == t2[d].row_off
 
 
 def _model_ops(oracle, p, t, pen, budget):

@@ -279,9 +279,6 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
 
     const int tid = G::tid();
     const int gsz = G::size();
-    const int lane = threadIdx.x & 31;
-    const int nwarps = WARP ? 1 : (int)(blockDim.x >> 5);
-    const int warp_in_group = WARP ? 0 : (int)(threadIdx.x >> 5);
     const int groups_per_cta = WARP ? (blockDim.x >> 5) : 1;
     const uint32_t group = blockIdx.x * groups_per_cta + G::id_in_cta();
 
@@ -446,39 +443,29 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                             R::st(aDc, k, NULLV);
                         }
                         const int width = 2 * n + 1;
-                        uint4 *rp = arena + st.row_off + warp_in_group;
-                        /* one diagonal per lane, 32 consecutive diagonals per warp iteration */
-                        for (int idc = tid; (idc - lane) < width; idc += gsz, rp += nwarps) {
-                            bool bI = false, bD = false, bM0 = false, bM1 = false;
-                            if (idc < width) {
-                                const int k = idc - n;
-                                const int io = R::ld(aMo, k - 1) + 1;
-                                const int ie = R::ld(aIe, k - 1) + 1;
-                                const int dopen = R::ld(aMo, k + 1);
-                                const int dext = R::ld(aDe, k + 1);
-                                const int X = R::ld(aMx, k) + 1;
-                                const int I = max(io, ie);
-                                const int D = max(dopen, dext);
-                                bI = ie >= io;                         /* extend beats open on ties */
-                                bD = dext >= dopen;
-                                /* D(3) beats X(2) beats I(1) on equal offsets */
-                                const int X4 = X * 4 + 2, I4 = I * 4 + 1;
-                                const int pM = max(max(X4, D * 4 + 3), I4);
-                                int M = pM >> 2;
-                                if (M >= 0) M = extend(k, M);
-                                R::st(aIc, k, I);
-                                R::st(aDc, k, D);
-                                R::st(aMc, k, M);
-                                bM0 = pM != X4;                        /* winner is I(1) or D(3) */
-                                bM1 = pM != I4;                        /* winner is X(2) or D(3) */
-                            }
-                            if (BT) {
-                                const uint32_t m0 = __ballot_sync(0xffffffffu, bI);
-                                const uint32_t m1 = __ballot_sync(0xffffffffu, bD);
-                                const uint32_t m2 = __ballot_sync(0xffffffffu, bM0);
-                                const uint32_t m3 = __ballot_sync(0xffffffffu, bM1);
-                                if (lane == 0) *rp = make_uint4(m0, m1, m2, m3);
-                            }
+                        /* one decision byte per cell: bit0 I extends, bit1 D extends, bits 3:2 the winner of M
+                         * (1 = I, 2 = X, 3 = D); a warp writes 32 consecutive bytes of the pair's row */
+                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + st.row_off);
+                        for (int idc = tid; idc < width; idc += gsz) {
+                            const int k = idc - n;
+                            const int io = R::ld(aMo, k - 1) + 1;
+                            const int ie = R::ld(aIe, k - 1) + 1;
+                            const int dopen = R::ld(aMo, k + 1);
+                            const int dext = R::ld(aDe, k + 1);
+                            const int X = R::ld(aMx, k) + 1;
+                            /* offset * 2 + tag: extend (1) beats open (0) on equal offsets */
+                            const int pI = max(io * 2, ie * 2 + 1);
+                            const int pD = max(dopen * 2, dext * 2 + 1);
+                            const int I = pI >> 1;
+                            const int D = pD >> 1;
+                            /* offset * 4 + tag: D(3) beats X(2) beats I(1) on equal offsets */
+                            const int pM = max(max(X * 4 + 2, D * 4 + 3), I * 4 + 1);
+                            int M = pM >> 2;
+                            if (M >= 0) M = extend(k, M);
+                            R::st(aIc, k, I);
+                            R::st(aDc, k, D);
+                            R::st(aMc, k, M);
+                            if (BT) rowb[idc] = (uint8_t)((pI & 1) | ((pD & 1) << 1) | ((pM & 3) << 2));
                         }
                     }
                     G::sync();
@@ -507,9 +494,8 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                         } else {
                             const int ii = ck + (int)st.n;
                             if (ii < 0 || ii > 2 * (int)st.n) { n_ops = 0; finished = false; break; }
-                            const uint4 dec = arena[st.row_off + (ii >> 5)];
-                            const int b = ii & 31;
-                            const int mop = (int)((dec.z >> b) & 1u) | (int)(((dec.w >> b) & 1u) << 1);
+                            const uint32_t dec = reinterpret_cast<const uint8_t *>(arena + st.row_off)[ii];
+                            const int mop = (int)(dec >> 2) & 3;
                             if (mop == OP_SUB) cd -= x;
                             else if (mop == OP_INS) comp = 1;
                             else comp = 2;
@@ -517,16 +503,15 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                     } else {
                         const int ii = ck + (int)st.n;
                         if (ii < 0 || ii > 2 * (int)st.n || st.kind != WFAGPU_STEP_MDI) { n_ops = 0; finished = false; break; }
-                        const uint4 dec = arena[st.row_off + (ii >> 5)];
-                        const int b = ii & 31;
+                        const uint32_t dec = reinterpret_cast<const uint8_t *>(arena + st.row_off)[ii];
                         if (comp == 1) {
                             op = OP_INS;
                             ck -= 1;
-                            if ((dec.x >> b) & 1u) cd -= e; else { cd -= oe; comp = 0; }
+                            if (dec & 1u) cd -= e; else { cd -= oe; comp = 0; }
                         } else {
                             op = OP_DEL;
                             ck += 1;
-                            if ((dec.y >> b) & 1u) cd -= e; else { cd -= oe; comp = 0; }
+                            if (dec & 2u) cd -= e; else { cd -= oe; comp = 0; }
                         }
                     }
                     word |= op << (2 * (n_ops & 15u));
@@ -789,40 +774,28 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
                             LO[2 * A + sM] = lo; HI[2 * A + sM] = hi;
                             if (BT) lo_tab[d] = lo;
                         }
-                        uint4 *rp = arena + st.row_off + warp;
+                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + st.row_off);
                         const int width = hi - lo + 1;
-                        for (int idc = tid; (idc - lane) < width; idc += gsz, rp += nwarps) {
-                            bool bI = false, bD = false, bM0 = false, bM1 = false;
-                            if (idc < width) {
-                                const int k = lo + idc;
-                                const int io = band_get(aMo, olo, ohi, k - 1) + 1;
-                                const int ie = band_get(aIe, ilo, ihi, k - 1) + 1;
-                                const int dopen = band_get(aMo, olo, ohi, k + 1);
-                                const int dext = band_get(aDe, dlo, dhi, k + 1);
-                                const int X = band_get(aMx, xlo, xhi, k) + 1;
-                                /* the reference keeps int16 values between the steps */
-                                const int I = (int)(short)max(io, ie);
-                                const int D = (int)(short)max(dopen, dext);
-                                bI = ie >= io;
-                                bD = dext >= dopen;
-                                const int X4 = (int)(short)X * 4 + 2, I4 = I * 4 + 1;
-                                const int pM = max(max(X4, D * 4 + 3), I4);
-                                int M = pM >> 2;
-                                if (M >= 0) M = extend(k, M);
-                                const uint32_t kk = (uint32_t)(2 * idc);
-                                sts_16(aIc + kk, I);
-                                sts_16(aDc + kk, D);
-                                sts_16(aMc + kk, M);
-                                bM0 = pM != X4;
-                                bM1 = pM != I4;
-                            }
-                            if (BT) {
-                                const uint32_t m0 = __ballot_sync(0xffffffffu, bI);
-                                const uint32_t m1 = __ballot_sync(0xffffffffu, bD);
-                                const uint32_t m2 = __ballot_sync(0xffffffffu, bM0);
-                                const uint32_t m3 = __ballot_sync(0xffffffffu, bM1);
-                                if (lane == 0) *rp = make_uint4(m0, m1, m2, m3);
-                            }
+                        for (int idc = tid; idc < width; idc += gsz) {
+                            const int k = lo + idc;
+                            const int io = band_get(aMo, olo, ohi, k - 1) + 1;
+                            const int ie = band_get(aIe, ilo, ihi, k - 1) + 1;
+                            const int dopen = band_get(aMo, olo, ohi, k + 1);
+                            const int dext = band_get(aDe, dlo, dhi, k + 1);
+                            const int X = band_get(aMx, xlo, xhi, k) + 1;
+                            /* the reference keeps int16 values between the steps */
+                            const int pI = max((int)(short)io * 2, (int)(short)ie * 2 + 1);
+                            const int pD = max(dopen * 2, dext * 2 + 1);
+                            const int I = pI >> 1;
+                            const int D = pD >> 1;
+                            const int pM = max(max((int)(short)X * 4 + 2, D * 4 + 3), I * 4 + 1);
+                            int M = pM >> 2;
+                            if (M >= 0) M = extend(k, M);
+                            const uint32_t kk = (uint32_t)(2 * idc);
+                            sts_16(aIc + kk, I);
+                            sts_16(aDc + kk, D);
+                            sts_16(aMc + kk, M);
+                            if (BT) rowb[idc] = (uint8_t)((pI & 1) | ((pD & 1) << 1) | ((pM & 3) << 2));
                         }
                     }
                     __syncthreads();
@@ -856,22 +829,21 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
                         if (st.kind != WFAGPU_STEP_MDI) { bad = true; break; }
                         const int ii = ck - lo_tab[cd];
                         if (ii < 0 || ii >= W) { bad = true; break; }
-                        const uint4 dec = arena[st.row_off + (ii >> 5)];
-                        const int b = ii & 31;
+                        const uint32_t dec = reinterpret_cast<const uint8_t *>(arena + st.row_off)[ii];
                         if (comp == 0) {
                             op = OP_SUB;
-                            const int mop = (int)((dec.z >> b) & 1u) | (int)(((dec.w >> b) & 1u) << 1);
+                            const int mop = (int)(dec >> 2) & 3;
                             if (mop == OP_SUB) cd = resolveM(cd - x);
                             else if (mop == OP_INS) comp = 1;
                             else comp = 2;
                         } else if (comp == 1) {
                             op = OP_INS;
                             ck -= 1;
-                            if ((dec.x >> b) & 1u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+                            if (dec & 1u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
                         } else {
                             op = OP_DEL;
                             ck += 1;
-                            if ((dec.y >> b) & 1u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+                            if (dec & 2u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
                         }
                     }
                     word |= op << (2 * (n_ops & 15u));

@@ -22,7 +22,8 @@ int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist, in
     int steps = 1; /* the reference counts the score-0 wavefront as step 1 (kernel.cu:580-581) */
     int n = 0;     /* half width of the computed diagonal range                                  */
     int mdi = 0;   /* number of M/I/D steps so far (the reference's wavefront growth)            */
-    const uint64_t band_units = banded_win > 0 ? (uint64_t)((banded_win + 31) / 32) : 0;
+    /* one decision byte per cell, rows padded to 16-byte units */
+    const uint64_t band_units = banded_win > 0 ? (uint64_t)((banded_win + 15) / 16) : 0;
     int d;
     has_m[0] = 1;
     if (tab) { tab[0].row_off = 0; tab[0].n = 0; tab[0].kind = WFAGPU_STEP_M; }
@@ -49,7 +50,7 @@ int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist, in
         } else if (m) { kind = WFAGPU_STEP_M; has_m[d] = 1; }
         if (units > 0xffffffffull) break;           /* row offsets are 32-bit */
         if (tab) { tab[d].row_off = (uint32_t)units; tab[d].n = (uint16_t)n; tab[d].kind = (uint16_t)kind; }
-        if (kind == WFAGPU_STEP_MDI) units += banded_win > 0 ? band_units : (uint64_t)((2 * n + 1 + 31) / 32);
+        if (kind == WFAGPU_STEP_MDI) units += banded_win > 0 ? band_units : (uint64_t)((2 * n + 1 + 15) / 16);
     }
     free(has_m);
     free(has_gap);
