@@ -453,19 +453,20 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                             const int dopen = R::ld(aMo, k + 1);
                             const int dext = R::ld(aDe, k + 1);
                             const int X = R::ld(aMx, k) + 1;
-                            /* offset * 2 + tag: extend (1) beats open (0) on equal offsets */
-                            const int pI = max(io * 2, ie * 2 + 1);
-                            const int pD = max(dopen * 2, dext * 2 + 1);
-                            const int I = pI >> 1;
-                            const int D = pD >> 1;
-                            /* offset * 4 + tag: D(3) beats X(2) beats I(1) on equal offsets */
-                            const int pM = max(max(X * 4 + 2, D * 4 + 3), I * 4 + 1);
-                            int M = pM >> 2;
+                            /* Offsets by plain max; the tie-breaks only decide the backtrace bits:
+                             * I/D: extend beats open on equal offsets; M: D beats X beats I. */
+                            const int I = max(io, ie);
+                            const int D = max(dopen, dext);
+                            int M = max(max(X, D), I);
+                            const bool bI = ie >= io;
+                            const bool bD = dext >= dopen;
+                            const bool bM0 = (D >= X) || (I > X);      /* winner is I(1) or D(3): not X */
+                            const bool bM1 = (D >= I) || (X >= I);      /* winner is X(2) or D(3): not I */
                             if (M >= 0) M = extend(k, M);
                             R::st(aIc, k, I);
                             R::st(aDc, k, D);
                             R::st(aMc, k, M);
-                            if (BT) rowb[idc] = (uint8_t)((pI & 1) | ((pD & 1) << 1) | ((pM & 3) << 2));
+                            if (BT) rowb[idc] = (uint8_t)((bI ? 1u : 0u) | (bD ? 2u : 0u) | (bM0 ? 4u : 0u) | (bM1 ? 8u : 0u));
                         }
                     }
                     G::sync();
