@@ -161,7 +161,7 @@ def run_ours(args):
     assert a.initialize_parameters(*PEN)
     a.options.max_error = MAX_ERROR
     a.options.compute_cigar = True
-    a.set_batch_size(max(1, PAIRS_PER_GPU // 2))          # two chunks: copy/compute/decode overlap
+    a.set_batch_size(max(1, PAIRS_PER_GPU // 4))          # four chunks: copies and text overlap the kernels
     gcells_total = sum(a.s.sequences_metadata[i].pattern_len * a.s.sequences_metadata[i].text_len
                        for i in range(a.num_pairs))
 

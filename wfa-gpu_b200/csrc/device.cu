@@ -250,8 +250,12 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
     /* packed layout + longest-first schedule */
     size_t words = 0;
     uint32_t max_len = 0;
+    uint64_t min_sum = ~0ull, max_sum = 0;
     for (size_t i = 0; i < n; ++i) {
         wfagpu_pair_t p = pairs[i];
+        const uint64_t sum = (uint64_t)p.plen + p.tlen;
+        min_sum = std::min(min_sum, sum);
+        max_sum = std::max(max_sum, sum);
         p.p_word = (uint32_t)words;
         words += packed_words_for(p.plen);
         p.t_word = (uint32_t)words;
@@ -267,7 +271,9 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
     }
     s.packed_words = words;
     s.max_len = max_len;
-    {
+    if ((uint64_t)min_sum * 8 < (uint64_t)max_sum * 7) {
+        /* longest first only pays when the lengths differ by more than ~12 %: for uniform
+         * reads the queue order is irrelevant and the sort would dominate the host time */
         const wfagpu_pair_t *hp = s.h_pairs.p;
         std::stable_sort(s.h_order.p, s.h_order.p + n, [hp](uint32_t a, uint32_t b) {
             return (uint64_t)hp[a].plen + hp[a].tlen > (uint64_t)hp[b].plen + hp[b].tlen;
