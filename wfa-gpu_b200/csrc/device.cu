@@ -458,7 +458,11 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         c.A = std::max(plan.o + plan.e, plan.x) + 1; c.E1 = plan.e + 1; c.G = c.A;
         c.seq_words = (int)packed_words_for(s.max_len);
         c.groups_per_cta = 1;
-        c.group_threads = std::min(1024, std::max(32, (win + 31) & ~31));
+        /* a few diagonals per thread: the per-score overhead (window bookkeeping, barrier) is paid
+         * per thread, and small CTAs let more pairs share an SM (measured on B200, W = 512:
+         * 512 threads 114 k, 256 threads 165 k, 128 threads 189 k pairs/s at 10 kbp / 5 %) */
+        c.group_threads = std::min(1024, std::max(64, ((win / 4) + 31) & ~31));
+        if (d->force_threads) c.group_threads = d->force_threads;
         c.stages = 2;
         c.smem = banded_smem_bytes(c.A, win, c.seq_words, c.stages);
         if (c.smem > d->prop.sharedMemPerBlockOptin) {

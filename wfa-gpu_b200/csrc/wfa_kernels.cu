@@ -707,7 +707,6 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
                     int lo, hi;
                     if (st.kind == WFAGPU_STEP_M) {
                         lo = xlo; hi = xhi;
-                        __syncthreads();                     /* everyone has read LO/HI before they change */
                         for (int k = lo + tid; k <= hi; k += gsz) {
                             int m = lds_s16(aMx + (uint32_t)(2 * (k - xlo))) + 1;
                             if (m >= 0) m = extend(k, m);
@@ -768,7 +767,8 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
                             lo = ctl->new_center - (W / 2);
                             hi = lo + W - 1;
                         }
-                        __syncthreads();                     /* sources' LO/HI are read; the slot may change now */
+                        /* nobody reads the window of the slot being rewritten during this score (it is
+                         * never one of its own sources: x, o+e, e < A), so it can be updated right away */
                         if (tid == 0) {
                             LO[sM] = lo; HI[sM] = hi;
                             LO[A + sM] = lo; HI[A + sM] = hi;
