@@ -209,3 +209,211 @@ int km_align_pair(const char *pattern, int plen, const char *text, int tlen,
     free(Mr); free(Ir); free(Dr); free(arena);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Checkpointed traceback (model of wfa_exact_kernel's CKPT mode).
+ *
+ * Instead of one decision byte per cell, the forward pass copies the ring rows (the last A
+ * scores of M, the last e+1 of I and D) every P scores.  The traceback then re-derives the
+ * offsets it needs: from the top cell (d_e, k_e) of a segment it loads the checkpoint c < d_e,
+ * recomputes scores c+1 .. d_e on the shrinking cone |k - k_e| <= d_e - d (every cell of the
+ * cone only depends on cells of the cone one level down, e >= 1, x >= 1), and walks the path
+ * inside the segment by comparing candidate offsets with the forward tie-breaks.  Work:
+ * ~ score * P cells per pair instead of a store per cell in the forward pass.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int A, E1, W, C, P;
+    const km_step_t *tab;
+    int x, o, e;
+    /* checkpoint j (score j*P): rows by age a: M[a] = M of score j*P - a */
+    int16_t **ckM, **ckI, **ckD;
+    /* segment scratch: rows by level i (score c + i), index k - klo */
+    int16_t *sM, *sI, *sD;
+    int c, klo, khi, R;
+    const char *pattern, *text;
+    int plen, tlen;
+    int16_t m00; /* M[0][0] */
+} km_tb_t;
+
+static int km_in_range(const km_tb_t *t, int d, int k)
+{
+    if (d < 0) return 0;
+    const int n = t->tab[d].n;
+    return k >= -n && k <= n;
+}
+
+/* offset of component comp (0 M, 1 I, 2 D) at (d, k) as the forward pass saw it */
+static int km_tb_get(const km_tb_t *t, int comp, int d, int k)
+{
+    if (d < 0 || !km_in_range(t, d, k)) return KM_NULL;
+    if (d > t->c) {
+        const int i = d - t->c;
+        if (k < t->klo || k > t->khi) return KM_NULL; /* outside the cone: never needed */
+        const int16_t *row = (comp == 0 ? t->sM : comp == 1 ? t->sI : t->sD) + (size_t)i * (t->khi - t->klo + 1);
+        return row[k - t->klo];
+    }
+    if (t->c == 0) {
+        /* checkpoint 0 is the initial state */
+        if (d == 0 && comp == 0 && k == 0) return t->m00;
+        return KM_NULL;
+    }
+    const int a = t->c - d, j = t->c / t->P;
+    if (comp == 0) { if (a >= t->A) return KM_NULL; return t->ckM[j][(size_t)a * t->W + t->C + k]; }
+    if (a >= t->E1) return KM_NULL;
+    return (comp == 1 ? t->ckI : t->ckD)[j][(size_t)a * t->W + t->C + k];
+}
+
+int km_align_pair_ckpt(const char *pattern, int plen, const char *text, int tlen,
+                       int x, int o, int e, const km_step_t *tab, int d_end, int n_cap, int period,
+                       int *finished, int *distance, uint8_t *ops_out, int ops_cap, int *n_ops, long *recomputed)
+{
+    const int A = imax(o + e, x) + 1, E1 = e + 1, G = A;
+    const int C = n_cap + 2 * G + 2, W = 2 * C + 1, P = period;
+    int16_t *Mr = (int16_t *)malloc((size_t)A * W * sizeof(int16_t));
+    int16_t *Ir = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
+    int16_t *Dr = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
+    const int n_ck = d_end / P + 2;
+    int16_t **ckM = (int16_t **)calloc((size_t)n_ck, sizeof(*ckM));
+    int16_t **ckI = (int16_t **)calloc((size_t)n_ck, sizeof(*ckI));
+    int16_t **ckD = (int16_t **)calloc((size_t)n_ck, sizeof(*ckD));
+    for (long i = 0; i < (long)A * W; i++) Mr[i] = 12345;
+    for (long i = 0; i < (long)E1 * W; i++) { Ir[i] = 12345; Dr[i] = 12345; }
+    for (int r = 0; r < A; r++) for (int k = -2 * G; k <= 2 * G; k++) Mr[r * W + C + k] = KM_NULL;
+    for (int r = 0; r < E1; r++) for (int k = -2 * G; k <= 2 * G; k++) { Ir[r * W + C + k] = KM_NULL; Dr[r * W + C + k] = KM_NULL; }
+    Mr[C] = (int16_t)km_extend(text, pattern, tlen, plen, 0, 0);
+    const int16_t m00 = Mr[C];
+    const int kt = tlen - plen;
+    int fin = 0, d = 0;
+    if (kt == 0 && Mr[C] == tlen) {
+        fin = 1;
+    } else {
+        for (d = 1; d < d_end; d++) {
+            const km_step_t st = tab[d];
+            const int n = st.n;
+            if (n > n_cap) break;
+            int16_t *Mc = Mr + (d % A) * W + C, *Ic = Ir + (d % E1) * W + C, *Dc = Dr + (d % E1) * W + C;
+            if (st.kind == KM_KIND_NULL) {
+                for (int k = -n - G; k <= n + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+            } else if (st.kind == KM_KIND_M) {
+                const int16_t *Mx = Mr + ((d - x) % A) * W + C;
+                for (int k = -n - G; k <= n + G; k++) {
+                    Ic[k] = KM_NULL; Dc[k] = KM_NULL;
+                    if (k < -n || k > n) { Mc[k] = KM_NULL; continue; }
+                    int m = Mx[k] + 1;
+                    if (m >= 0) m = km_extend(text, pattern, tlen, plen, k, m);
+                    Mc[k] = (int16_t)m;
+                }
+            } else {
+                const int16_t *Mo = Mr + ((((d - o - e) % A) + A) % A) * W + C;
+                const int16_t *Ie = Ir + ((((d - e) % E1) + E1) % E1) * W + C;
+                const int16_t *De = Dr + ((((d - e) % E1) + E1) % E1) * W + C;
+                const int16_t *Mxx = Mr + ((((d - x) % A) + A) % A) * W + C;
+                for (int k = -n - G; k < -n; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+                for (int k = n + 1; k <= n + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+                for (int k = -n; k <= n; k++) {
+                    const int I = imax(Mo[k - 1] + 1, Ie[k - 1] + 1);
+                    const int D = imax(Mo[k + 1], De[k + 1]);
+                    int M = imax(imax(Mxx[k] + 1, D), I);
+                    if (M >= 0) M = km_extend(text, pattern, tlen, plen, k, M);
+                    Ic[k] = (int16_t)I; Dc[k] = (int16_t)D; Mc[k] = (int16_t)M;
+                }
+            }
+            const int done = (st.kind != KM_KIND_NULL) && kt >= -n && kt <= n && Mc[kt] == tlen;
+            if (!done && d % P == 0) {
+                /* checkpoint: ring rows by age */
+                const int j = d / P;
+                ckM[j] = (int16_t *)malloc((size_t)A * W * sizeof(int16_t));
+                ckI[j] = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
+                ckD[j] = (int16_t *)malloc((size_t)E1 * W * sizeof(int16_t));
+                for (int a = 0; a < A; a++)
+                    memcpy(ckM[j] + (size_t)a * W, Mr + ((((d - a) % A) + A) % A) * W, (size_t)W * sizeof(int16_t));
+                for (int a = 0; a < E1; a++) {
+                    memcpy(ckI[j] + (size_t)a * W, Ir + ((((d - a) % E1) + E1) % E1) * W, (size_t)W * sizeof(int16_t));
+                    memcpy(ckD[j] + (size_t)a * W, Dr + ((((d - a) % E1) + E1) % E1) * W, (size_t)W * sizeof(int16_t));
+                }
+            }
+            if (done) { fin = 1; break; }
+        }
+    }
+    *finished = fin;
+    *distance = fin ? d : 0;
+    *n_ops = 0;
+    long rec = 0;
+    int rc = 0;
+    if (fin && d > 0) {
+        km_tb_t t;
+        memset(&t, 0, sizeof(t));
+        t.A = A; t.E1 = E1; t.W = W; t.C = C; t.P = P; t.tab = tab; t.x = x; t.o = o; t.e = e;
+        t.ckM = ckM; t.ckI = ckI; t.ckD = ckD; t.pattern = pattern; t.text = text; t.plen = plen; t.tlen = tlen;
+        t.m00 = m00;
+        const int SW = 2 * P + 3;
+        t.sM = (int16_t *)malloc((size_t)(P + 2) * SW * sizeof(int16_t));
+        t.sI = (int16_t *)malloc((size_t)(P + 2) * SW * sizeof(int16_t));
+        t.sD = (int16_t *)malloc((size_t)(P + 2) * SW * sizeof(int16_t));
+        int cd = d, ck = kt, comp = 0, cnt = 0;
+        while (!(comp == 0 && cd == 0) && rc == 0) {
+            if (cd <= 0) { rc = -1; break; }
+            /* ---- open the segment that contains (cd, ck) ---- */
+            const int c = ((cd - 1) / P) * P;
+            const int R = cd - c;
+            t.c = 0;  /* while filling, read sources through the same accessor: set bounds first */
+            t.klo = ck - R; t.khi = ck + R; t.R = R;
+            const int sw = t.khi - t.klo + 1;
+            t.c = c;
+            for (int i = 1; i <= R; i++) {
+                const int dd = c + i;
+                const km_step_t st = tab[dd];
+                int16_t *rm = t.sM + (size_t)i * sw, *ri = t.sI + (size_t)i * sw, *rd = t.sD + (size_t)i * sw;
+                for (int k = t.klo; k <= t.khi; k++) { rm[k - t.klo] = KM_NULL; ri[k - t.klo] = KM_NULL; rd[k - t.klo] = KM_NULL; }
+                if (st.kind == KM_KIND_NULL) continue;
+                const int half = R - i;
+                for (int k = ck - half; k <= ck + half; k++) {
+                    if (!km_in_range(&t, dd, k)) continue;
+                    rec++;
+                    if (st.kind == KM_KIND_M) {
+                        int m = km_tb_get(&t, 0, dd - x, k) + 1;
+                        if (m >= 0) m = km_extend(text, pattern, tlen, plen, k, m);
+                        rm[k - t.klo] = (int16_t)m;
+                    } else {
+                        const int I = imax(km_tb_get(&t, 0, dd - o - e, k - 1) + 1, km_tb_get(&t, 1, dd - e, k - 1) + 1);
+                        const int D = imax(km_tb_get(&t, 0, dd - o - e, k + 1), km_tb_get(&t, 2, dd - e, k + 1));
+                        int M = imax(imax(km_tb_get(&t, 0, dd - x, k) + 1, D), I);
+                        if (M >= 0) M = km_extend(text, pattern, tlen, plen, k, M);
+                        ri[k - t.klo] = (int16_t)I; rd[k - t.klo] = (int16_t)D; rm[k - t.klo] = (int16_t)M;
+                    }
+                }
+            }
+            /* ---- walk the path while it stays above the checkpoint ---- */
+            while (cd > c && !(comp == 0 && cd == 0)) {
+                if (cnt >= ops_cap) { rc = -1; break; }
+                const km_step_t st = tab[cd];
+                if (comp == 0) {
+                    ops_out[cnt++] = 2;
+                    if (st.kind == KM_KIND_M) { cd -= x; continue; }
+                    const int X = km_tb_get(&t, 0, cd - x, ck) + 1;
+                    const int I = km_tb_get(&t, 1, cd, ck), D = km_tb_get(&t, 2, cd, ck);
+                    if (D >= X && D >= I) comp = 2;          /* D beats X beats I */
+                    else if (X >= I) cd -= x;
+                    else comp = 1;
+                } else if (comp == 1) {
+                    ops_out[cnt++] = 1;
+                    const int op = km_tb_get(&t, 0, cd - o - e, ck - 1) + 1, ex = km_tb_get(&t, 1, cd - e, ck - 1) + 1;
+                    ck -= 1;
+                    if (ex >= op) cd -= e; else { cd -= o + e; comp = 0; }   /* extend beats open */
+                } else {
+                    ops_out[cnt++] = 3;
+                    const int op = km_tb_get(&t, 0, cd - o - e, ck + 1), ex = km_tb_get(&t, 2, cd - e, ck + 1);
+                    ck += 1;
+                    if (ex >= op) cd -= e; else { cd -= o + e; comp = 0; }
+                }
+            }
+        }
+        *n_ops = cnt;
+        free(t.sM); free(t.sI); free(t.sD);
+    }
+    if (recomputed) *recomputed = rec;
+    for (int j = 0; j < n_ck; j++) { free(ckM[j]); free(ckI[j]); free(ckD[j]); }
+    free(ckM); free(ckI); free(ckD);
+    free(Mr); free(Ir); free(Dr);
+    return rc;
+}

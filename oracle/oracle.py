@@ -58,6 +58,9 @@ class Oracle:
         L.orc_align_chain.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 6 + [
             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]
         L.km_build_steps.argtypes = [C.c_int] * 5 + [C.POINTER(KmStep), C.POINTER(C.c_uint64)]
+        L.km_align_pair_ckpt.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 3 + [
+            C.POINTER(KmStep), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+            C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_long)]
         L.km_align_pair.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 3 + [
             C.POINTER(KmStep), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
             C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_long)]
@@ -110,6 +113,25 @@ class Oracle:
         s = C.string_at(out).decode()
         self.L.orc_free(out)
         return s
+
+    def model_align_ckpt(self, pattern, text, x, o, e, max_steps, period=32):
+        """CPU model of the checkpointed traceback (ring snapshots every `period` scores +
+        recomputation on the dependency cone)."""
+        p, t = _b(pattern), _b(text)
+        max_dist = max_steps * (max(x, o + e) + 2) + 16
+        tab = (KmStep * (max_dist + 1))()
+        words = C.c_uint64()
+        d_end = self.L.km_build_steps(x, o, e, max_steps, max_dist, tab, C.byref(words))
+        fin, dist, nops, rec = C.c_int(), C.c_int(), C.c_int(), C.c_long()
+        cap = 2 * d_end + 16
+        ops = (C.c_uint8 * cap)()
+        rc = self.L.km_align_pair_ckpt(p, len(p), t, len(t), x, o, e, tab, d_end, max_steps, period,
+                                       C.byref(fin), C.byref(dist), ops, cap, C.byref(nops), C.byref(rec))
+        assert rc == 0, "checkpointed traceback failed"
+        cg = None
+        if fin.value:
+            cg = self.decode_ops(pattern, text, dist.value, list(ops[: nops.value])[::-1])
+        return dict(finished=bool(fin.value), distance=dist.value, cigar=cg, recomputed=rec.value)
 
     # -- CPU model of the B200 kernel's algorithm ------------------------------
     def model_align(self, pattern, text, x, o, e, max_steps, cigar=True, n_cap=None):

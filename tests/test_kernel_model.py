@@ -1,6 +1,7 @@
 """The CPU model of the B200 kernel's data flow (oracle/kernel_model.c: penalty-only step
-table, clean rings with NULL guards, decision bit-planes + traceback) must give exactly
-what the faithful restatement gives.  CPU only."""
+table, clean rings with NULL guards, decision bytes + traceback, and the checkpointed
+traceback that recomputes offsets from ring snapshots) must give exactly what the faithful
+restatement gives.  CPU only."""
 import pytest
 
 from test_oracle_ref import make_pairs, PENS
@@ -13,6 +14,20 @@ def test_model_equals_oracle(oracle, pen):
     for p, t in pairs:
         r = oracle.align(p, t, *pen, 1200)
         m = oracle.model_align(p, t, *pen, 1200)
+        assert r["finished"]
+        assert (m["finished"], m["distance"], m["cigar"]) == (r["finished"], r["distance"], r["cigar"])
+
+
+@pytest.mark.parametrize("period", [4, 7, 16, 32])
+@pytest.mark.parametrize("pen", PENS + [(1, 0, 1), (3, 5, 2), (7, 11, 3), (2, 24, 9)])
+def test_checkpointed_traceback_equals_oracle(oracle, pen, period):
+    # ring snapshots every `period` scores + recomputation on the dependency cone
+    # (the exact kernel's CIGAR path, wfa_traceback_kernel) -- same CIGARs as the reference walk
+    pairs = make_pairs(7, [(150, 0.05, 30), (700, 0.1, 6), (25, 0.35, 40), (0, 0, 1)])
+    pairs += [("", "ACGT"), ("ACGT", ""), ("ACGT", "ACGT"), ("A", "C"), ("ACGTACGTAC", "TTTTTTTTTT")]
+    for p, t in pairs:
+        r = oracle.align(p, t, *pen, 1200)
+        m = oracle.model_align_ckpt(p, t, *pen, 1200, period)
         assert r["finished"]
         assert (m["finished"], m["distance"], m["cigar"]) == (r["finished"], r["distance"], r["cigar"])
 

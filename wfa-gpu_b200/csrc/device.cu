@@ -79,7 +79,7 @@ struct PinBuf {
     }
 };
 
-enum { CTR_QUEUE = 0, CTR_POOL = 1, CTR_RETRY = 2, CTR_ASCII = 3, CTR_WORDS = 8 };
+enum { CTR_QUEUE = 0, CTR_POOL = 1, CTR_RETRY = 2, CTR_ASCII = 3, CTR_TBQ = 4, CTR_WORDS = 8 };
 
 struct LaunchCfg {
     int group_threads;   /* 32 = warp per pair */
@@ -92,6 +92,7 @@ struct LaunchCfg {
     size_t smem;
     int A, E1, G;
     bool global_ring;     /* large tier: rings in global memory, int32 offsets */
+    bool ckpt;            /* checkpointed traceback (ring snapshots) instead of decision bytes */
 };
 
 struct Slot {
@@ -116,6 +117,10 @@ struct Slot {
     PinBuf<wfagpu_cigar_ref_t> h_refs;
     PinBuf<unsigned long long> h_heads;
     DevBuf<wfagpu_step_t> steps;
+    DevBuf<uint32_t> ck_off;           /* arena offset of every ring snapshot (checkpointed traceback) */
+    std::vector<uint64_t> h_ck_off;    /* [j] = units used by the snapshots of scores < j * period */
+    PinBuf<uint32_t> h_ck32;
+    int ck_key[1] = {-1};              /* period the offsets were built for */
     PinBuf<wfagpu_pair_t> h_pairs;
     PinBuf<uint32_t> h_order;
     PinBuf<wfagpu_pair_out_t> h_out;
@@ -146,6 +151,8 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
+    bool no_ckpt = false;
+    int force_period = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
     int hint_dist = 0;
     int hint_key[3] = {-1, -1, -1};
@@ -203,6 +210,9 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->force_stages = env_int("WFAGPU_STAGES", 0);
     d->force_ctas_per_sm = env_int("WFAGPU_CTAS_PER_SM", 0);
     d->force_warp = env_int("WFAGPU_WARP_KERNEL", -1);
+    d->no_ckpt = env_int("WFAGPU_NO_CKPT", 0) != 0;
+    d->force_period = env_int("WFAGPU_CK_PERIOD", 0);
+    if (d->force_period != 8 && d->force_period != 16 && d->force_period != 32) d->force_period = 0;
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
     d->force_large = env_int("WFAGPU_FORCE_LARGE", 0) != 0;
     d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;
@@ -219,7 +229,7 @@ extern "C" void wfagpu_device_close_all(void)
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.ascii.release(); s.packed.release(); s.pairs.release(); s.order.release();
             s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
-            s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release();
+            s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release(); s.ck_off.release(); s.h_ck32.release();
             s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release(); s.slots.release(); s.text.release(); s.refs.release(); s.heads.release();
             s.h_text.release(); s.h_refs.release(); s.h_heads.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
@@ -311,9 +321,14 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
     const int seq_words = (int)packed_words_for(max_len);
     c->A = A; c->E1 = E1; c->G = G; c->seq_words = seq_words;
     n_want = std::max(1, n_want);
-    auto rs = [&](int ncap) { return 2 * (ncap + 2 * G + 1) + 2; };
+    /* ring row geometry.  Checkpointed traceback copies rows in 16-byte units: diagonal 0 sits on
+     * an 8-element boundary and a row has 8 spare cells on both sides. */
+    bool ck = false;
+    auto ctr = [&](int ncap) { return ck ? ((ncap + 2 * G + 8 + 7) & ~7) : ncap + 2 * G + 1; };
+    auto rs = [&](int ncap) { return ck ? 2 * ctr(ncap) : 2 * (ncap + 2 * G + 1) + 2; };
 
     c->global_ring = false;
+    c->ckpt = false;
     bool large = d->force_large || max_len >= (1u << 15);
     if (!large) {
         /* rings that do not fit one CTA's shared memory even single-buffered go to the large tier */
@@ -357,6 +372,8 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
     }
     if (!warp) {
         c->groups_per_cta = 1;
+        ck = bt && !d->no_ckpt;
+        c->ckpt = ck;
         int best_k = 0, stages = 1, n_cap = n_want;
         size_t smem = 0;
         const int kmax = d->force_ctas_per_sm ? d->force_ctas_per_sm : 6;
@@ -374,7 +391,7 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
             stages = 1;
             const size_t fixed = exact_smem_bytes(A, E1, 0, seq_words, 1, stages);
             if (fixed + (size_t)rows * rs(1) * 2 > smem_max) return -2;   /* the sequences alone do not fit */
-            n_cap = (int)((smem_max - fixed - 64) / ((size_t)rows * 4)) - 2 * G - 2;
+            n_cap = (int)((smem_max - fixed - 64) / ((size_t)rows * 4)) - 2 * G - (ck ? 16 : 2);
             if (n_cap < 1) return -2;
             smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
             best_k = 1;
@@ -382,7 +399,7 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
         c->stages = stages;
         c->n_cap = n_cap;
         c->row_stride = rs(n_cap);
-        c->center = n_cap + 2 * G + 1;
+        c->center = ctr(n_cap);
         c->smem = smem;
         /* about 1152 threads per SM in total, never more threads than half the widest wavefront */
         int t = best_k == 1 ? 1024 : (best_k == 2 ? 512 : ((1152 / best_k) / 32) * 32);
@@ -393,7 +410,7 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
         c->group_threads = t;
     }
     const int threads = warp ? 32 * c->groups_per_cta : c->group_threads;
-    int occ = exact_max_ctas_per_sm(c->group_threads, c->groups_per_cta, c->smem, ascii, bt);
+    int occ = exact_max_ctas_per_sm(c->group_threads, c->groups_per_cta, c->smem, ascii, bt, c->ckpt);
     if (occ < 1) {
         fprintf(stderr, "[wfagpu] kernel configuration does not fit (threads=%d smem=%zu)\n", threads, c->smem);
         return -1;
@@ -416,6 +433,36 @@ static void learn_hint(wfagpu_device *d, Slot &s, size_t n)
     d->hint_key[0] = s.plan.x; d->hint_key[1] = s.plan.o; d->hint_key[2] = s.plan.e;
 }
 
+/* Ring-snapshot layout of the checkpointed traceback for period P: snapshot j (score j * P) holds
+ * (A-1) + 2e rows of the 16-byte units that cover [-n, n] at that score.  h_ck_off[j] = units used
+ * by the snapshots before j. */
+static int ensure_ck_table(Slot &s, const wfagpu_plan_t &plan, int period)
+{
+    if (s.ck_key[0] == period) return 0;
+    const int de = s.tab_d_end;
+    const int A = std::max(plan.o + plan.e, plan.x) + 1;
+    const uint64_t rows_ck = (uint64_t)(A - 1 + 2 * plan.e);
+    const int n_ck = (de - 1) / period + 2;
+    s.h_ck_off.assign((size_t)n_ck + 1, 0);
+    if (s.h_ck32.ensure((size_t)n_ck + 1)) return -1;
+    CK(cudaStreamSynchronize(s.stream));      /* an earlier pass may still be reading the pinned copy */
+    uint64_t acc = 0;
+    s.h_ck32.p[0] = 0;
+    for (int j = 1; j <= n_ck; ++j) {
+        s.h_ck_off[j] = acc;
+        s.h_ck32.p[j] = (uint32_t)std::min<uint64_t>(acc, 0xffffffffu);
+        const long long dj = (long long)j * period;
+        if (dj < de) {
+            const int n = s.h_steps.p[dj].n;
+            acc += rows_ck * (uint64_t)((((n + 7) & ~7) + ((n + 8) & ~7)) >> 3);
+        }
+    }
+    if (s.ck_off.ensure((size_t)n_ck + 1)) return -1;
+    CK(cudaMemcpyAsync(s.ck_off.p, s.h_ck32.p, ((size_t)n_ck + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    s.ck_key[0] = period;
+    return 0;
+}
+
 /* Launch one pass over `n_items` entries of `order_dev`. */
 static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int max_steps, const uint32_t *order_dev,
                        size_t n_items, uint32_t *retry_dev, bool ascii, bool first_pass, bool use_hint,
@@ -436,6 +483,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = max_steps; s.tab_key[4] = tab_win;
         s.tab_d_end = de;
         s.tab_arena_units = units;
+        s.ck_key[0] = -1;     /* snapshot offsets follow the table */
     }
     const wfagpu_step_t *tab = s.h_steps.p;
     const int d_full = s.tab_d_end;
@@ -494,23 +542,51 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         arena_units = d_end < d_full ? tab[d_end].row_off : s.tab_arena_units;
     }
     *capped_out = c.n_cap < n_full;
-
-    if (!plan.with_cigar) arena_units = 0;
+    /* memory budget of the arenas: a third of the free device memory */
+    size_t arena_budget = 0;
     {
-        /* keep the decision arenas within a third of the free device memory: fewer, not smaller, groups */
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const size_t have = s.arena.cap * sizeof(uint4);
-        const size_t budget = std::max<size_t>((free_b + have) / 3, (size_t)64 << 20);
-        const size_t per_group = (size_t)arena_units * sizeof(uint4) * (size_t)c.groups_per_cta + 1;
-        const size_t max_ctas = std::max<size_t>(1, budget / per_group);
-        if ((size_t)c.ctas > max_ctas) c.ctas = (int)max_ctas;
+        arena_budget = std::max<size_t>((free_b + s.arena.cap * sizeof(uint4)) / 3, (size_t)64 << 20);
+    }
+    int period = 0;
+    if (c.ckpt) {
+        /* Snapshot period: the traceback recomputes ~ score * P cells per pair against ~ score^2 in
+         * the forward pass, the snapshots take ~ 1/P of the cells: short periods for low scores,
+         * longer ones when memory is tight. */
+        const int d_expect = (n_want < n_full) ? std::min(d_end, d->hint_dist + 1) : d_end;
+        period = d->force_period ? d->force_period : (d_expect >= 3000 ? 32 : 16);   /* measured on B200: 8 never wins */
+        for (;;) {
+            if (ensure_ck_table(s, plan, period)) return -1;
+            arena_units = s.h_ck_off[(size_t)(d_end - 1) / period + 1];      /* snapshots of scores j * P < d_end */
+            if (period >= 32 || d->force_period || (arena_units * sizeof(uint4) + 1) * n_items <= arena_budget) break;
+            period *= 2;
+        }
+        if (arena_units >= 0xffffffffull) { fprintf(stderr, "[wfagpu] snapshot arena exceeds 32-bit offsets\n"); return -1; }
+    }
+
+    if (!plan.with_cigar) arena_units = 0;
+    /* keep the arenas within a third of the free device memory: fewer, not smaller, groups
+     * (decision bytes: one arena per resident group; snapshots: one per pair of a sub-launch) */
+    size_t items_per_launch = n_items;
+    {
+        const size_t budget = arena_budget;
+        if (c.ckpt) {
+            const size_t per_pair = (size_t)arena_units * sizeof(uint4) + 1;
+            items_per_launch = std::max<size_t>(1, std::min<size_t>(n_items, budget / per_pair));
+            c.ctas = (int)std::min<size_t>((size_t)c.ctas, items_per_launch);
+        } else {
+            const size_t per_group = (size_t)arena_units * sizeof(uint4) * (size_t)c.groups_per_cta + 1;
+            const size_t max_ctas = std::max<size_t>(1, budget / per_group);
+            if ((size_t)c.ctas > max_ctas) c.ctas = (int)max_ctas;
+        }
     }
     const size_t groups = (size_t)c.ctas * c.groups_per_cta;
     const uint64_t gring_elems = c.global_ring ? (uint64_t)(c.A + 2 * c.E1) * (uint64_t)c.row_stride : 0;
     if (s.gring.ensure(groups * gring_elems + 1)) return -1;
     const uint32_t scratch_words = plan.with_cigar ? (uint32_t)((2 * (size_t)d_end + 31) / 16 + 2) : 1;
-    if (s.arena.ensure(groups * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
+    const size_t arenas = c.ckpt ? items_per_launch : groups;
+    if (s.arena.ensure(arenas * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
     const uint32_t band_lo_words = (banded && plan.with_cigar) ? (uint32_t)d_end + 1 : 0;
     if (s.band_lo.ensure(groups * (size_t)band_lo_words + 1)) return -1;
     /* op pool: worst case for this pass on top of what is already used */
@@ -523,7 +599,6 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     }
     if (s.pool.ensure(pool_need, true, s.stream)) return -1;
 
-    CK(cudaMemsetAsync(s.counters.p + CTR_QUEUE, 0, sizeof(uint32_t), s.stream));
     CK(cudaMemsetAsync(s.counters.p + CTR_RETRY, 0, sizeof(uint32_t), s.stream));
 
     KernelParams kp{};
@@ -533,6 +608,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.order = order_dev;
     kp.n_items = (uint32_t)n_items;
     kp.queue = s.counters.p + CTR_QUEUE;
+    kp.tb_queue = s.counters.p + CTR_TBQ;
     kp.steps = s.steps.p;
     kp.d_end = d_end;
     kp.n_cap = c.n_cap;
@@ -551,6 +627,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.gring_elems = gring_elems;
     kp.arena = s.arena.p;
     kp.arena_units = arena_units;
+    kp.ck_off = c.ckpt ? s.ck_off.p : nullptr;
+    kp.ck_period = period;
     kp.ops_scratch = s.scratch.p;
     kp.ops_scratch_words = scratch_words;
     kp.ops_pool = s.pool.p;
@@ -563,16 +641,40 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.ascii_count = s.counters.p + CTR_ASCII;
     kp.cells = d->count_cells ? s.cells.p : nullptr;
     if (env_int("WFAGPU_VERBOSE", 0))
-        fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d band=%d tier=%s arena=%.1f MB\n",
+        fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d band=%d tier=%s period=%d arena=%.1f MB\n",
                 n_items, max_steps, c.n_cap, d_end, c.group_threads, c.groups_per_cta, c.ctas, c.stages, c.smem,
-                (int)ascii, plan.band > 0 ? win : 0, c.global_ring ? "global-int32" : "smem-int16", groups * arena_units * 16.0 / 1e6);
-    cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
-                           : launch_exact(kp, c.group_threads, c.groups_per_cta, c.ctas, c.smem, ascii, s.stream);
-    if (e != cudaSuccess) {
-        fprintf(stderr, "[wfagpu] alignment kernel launch failed: %s\n", cudaGetErrorString(e));
-        return -1;
+                (int)ascii, plan.band > 0 ? win : 0, c.global_ring ? "global-int32" : (c.ckpt ? "smem-int16+ckpt" : "smem-int16"), period, arenas * arena_units * 16.0 / 1e6);
+    int tb_ctas = 0;
+    constexpr int kTbWarps = 8;
+    if (c.ckpt) {
+        const int occ = traceback_max_ctas_per_sm(c.A, period, kTbWarps, ascii);
+        if (occ < 1) { fprintf(stderr, "[wfagpu] traceback kernel does not fit\n"); return -1; }
+        tb_ctas = occ * d->prop.multiProcessorCount;
     }
-    s.stats.launches += 1;
+    for (size_t off = 0; off < n_items; off += items_per_launch) {
+        const size_t cnt = std::min(items_per_launch, n_items - off);
+        kp.order = order_dev + off;
+        kp.n_items = (uint32_t)cnt;
+        CK(cudaMemsetAsync(s.counters.p + CTR_QUEUE, 0, sizeof(uint32_t), s.stream));
+        cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
+                               : launch_exact(kp, c.group_threads, c.groups_per_cta, (int)std::min<size_t>(c.ctas, cnt), c.smem, ascii, s.stream);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "[wfagpu] alignment kernel launch failed: %s\n", cudaGetErrorString(e));
+            return -1;
+        }
+        s.stats.launches += 1;
+        if (c.ckpt) {
+            /* ring snapshots -> 2-bit ops, a warp per pair */
+            CK(cudaMemsetAsync(s.counters.p + CTR_TBQ, 0, sizeof(uint32_t), s.stream));
+            const int ctas = (int)std::min<size_t>((size_t)tb_ctas, (cnt + kTbWarps - 1) / kTbWarps);
+            e = launch_traceback(kp, ctas, kTbWarps, ascii, s.stream);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "[wfagpu] traceback kernel launch failed: %s\n", cudaGetErrorString(e));
+                return -1;
+            }
+            s.stats.launches += 1;
+        }
+    }
     s.last_d_end = std::max(s.last_d_end, d_end);
     s.text_queued = false;
     return 0;

@@ -178,6 +178,12 @@ __device__ __forceinline__ void sts_16(uint32_t a, int v)
 {
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory");
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 
 /* Where the wavefront rings live.  RingS16: shared memory, int16 offsets (sequences
  * < 32768 bases, the reference's wfa_offset_t).  RingG32: global memory (L2), int32
@@ -266,11 +272,18 @@ struct GroupCtl {
     uint32_t idx[2];     /* pair index staged in each buffer                */
     uint32_t n_ops;
     uint32_t ops_off;
+    uint32_t pos[2];     /* queue position of that pair (its snapshot arena) */
+    uint32_t pad[2];
 };
 
-template <bool WARP, bool ASCII, bool BT, typename R>
+/* CKPT (CTA per pair, shared-memory rings, with backtrace): instead of a decision byte per
+ * cell the forward pass snapshots the ring rows every p.ck_period scores, and the traceback
+ * recomputes the offsets it needs on the dependency cone below the cell it stands on
+ * (model + proof of equivalence: oracle/kernel_model.c, km_align_pair_ckpt). */
+template <bool WARP, bool ASCII, bool BT, typename R, bool CKPT>
 __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const __grid_constant__ KernelParams p)
 {
+    static_assert(!CKPT || (BT && !WARP && R::kElem == 2), "checkpointed traceback: CTA groups with shared-memory rings");
     using G = Group<WARP>;
     using RA = typename R::addr_t;
     constexpr bool GR = (R::kElem == 4);          /* rings in global memory */
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
     const RA I0 = R::add(M0, (uint32_t)A * row_bytes);
     const RA D0 = R::add(I0, (uint32_t)E1 * row_bytes);
 
-    uint4 *const arena = p.arena + (size_t)group * p.arena_units;
+    uint4 *arena = p.arena + (size_t)group * p.arena_units;    /* CKPT: one arena per pair, set below */
     uint32_t *const scratch = p.ops_scratch + (size_t)group * p.ops_scratch_words;
 
     auto issue_load = [&](int stage, uint32_t idx) {
@@ -321,8 +334,9 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         tma_load_1d(dp, p.packed + pr.p_word, pw * 4u, &ctl->bar[stage]);
         tma_load_1d(dt, p.packed + pr.t_word, tw * 4u, &ctl->bar[stage]);
     };
-    auto pop = [&]() -> uint32_t {
+    auto pop = [&](int slot) -> uint32_t {
         const uint32_t pos = atomicAdd(p.queue, 1u);
+        ctl->pos[slot] = pos;
         return pos < p.n_items ? p.order[pos] : kInvalidIdx;
     };
 
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
             mbar_init(&ctl->bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        const uint32_t first = pop();
+        const uint32_t first = pop(0);
         ctl->idx[0] = first;
         if (first != kInvalidIdx) issue_load(0, first);
     }
@@ -344,9 +358,10 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
     while (true) {
         const uint32_t idx = ctl->idx[stage];
         if (idx == kInvalidIdx) break;
+        if (CKPT) arena = p.arena + (size_t)ctl->pos[stage] * p.arena_units;
         if (tid == 0 && p.stages == 2) {
             /* prefetch the next pair into the other stage while this one computes */
-            const uint32_t nxt = pop();
+            const uint32_t nxt = pop(stage ^ 1);
             ctl->idx[stage ^ 1] = nxt;
             if (nxt != kInvalidIdx) issue_load(stage ^ 1, nxt);
         }
@@ -401,6 +416,34 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                 RA aMo = R::add(M0, (uint32_t)((A - oe % A) % A) * row_bytes);      /* row of score d - o - e */
                 RA aIe = R::add(I0, (uint32_t)((E1 - e % E1) % E1) * row_bytes);    /* row of score d - e     */
                 RA aDe = R::add(D0, (uint32_t)((E1 - e % E1) % E1) * row_bytes);
+                int ck_left = p.ck_period, ck_j = 0;
+                /* snapshot of the ring rows the scores above d can still read: M of scores d .. d-A+2,
+                 * I and D of d .. d-e+1, each over [-n, n] rounded out to 16-byte units */
+                auto checkpoint = [&](int n) {
+                    if constexpr (CKPT) {
+                        const int k0 = -((n + 7) & ~7);
+                        const int units = (((n + 7) & ~7) + ((n + 8) & ~7)) >> 3;
+                        uint4 *dst = arena + p.ck_off[ck_j];
+                        uint32_t row = (uint32_t)aMc;
+                        for (int a = 0; a < A - 1; ++a) {
+                            for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
+                            dst += units;
+                            row = (row == (uint32_t)M0) ? (uint32_t)Mend - row_bytes : row - row_bytes;
+                        }
+                        row = (uint32_t)aIc;
+                        for (int a = 0; a < e; ++a) {
+                            for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
+                            dst += units;
+                            row = (row == (uint32_t)I0) ? (uint32_t)Iend - row_bytes : row - row_bytes;
+                        }
+                        row = (uint32_t)aDc;
+                        for (int a = 0; a < e; ++a) {
+                            for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
+                            dst += units;
+                            row = (row == (uint32_t)D0) ? (uint32_t)Dend - row_bytes : row - row_bytes;
+                        }
+                    }
+                };
                 for (int d = 1; d < p.d_end; ++d) {
                     const wfagpu_step_t st = st_next;
                     if (d + 1 < p.d_end) st_next = p.steps[d + 1];
@@ -421,6 +464,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                             R::st(aDc, k, NULLV);
                         }
                         G::sync();
+                        if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n); }
                         continue;
                     }
                     if (st.kind == WFAGPU_STEP_M) {
@@ -466,7 +510,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                             R::st(aIc, k, I);
                             R::st(aDc, k, D);
                             R::st(aMc, k, M);
-                            if (BT) rowb[idc] = (uint8_t)((bI ? 1u : 0u) | (bD ? 2u : 0u) | (bM0 ? 4u : 0u) | (bM1 ? 8u : 0u));
+                            if (BT && !CKPT) rowb[idc] = (uint8_t)((bI ? 1u : 0u) | (bD ? 2u : 0u) | (bM0 ? 4u : 0u) | (bM1 ? 8u : 0u));
                         }
                     }
                     G::sync();
@@ -475,14 +519,17 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                         dist = d;
                         break;
                     }
+                    if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n); }
                 }
             }
         }
 
-        /* ---- traceback (leader): decision planes -> 2-bit ops, newest first ---- */
+        /* ---- traceback -> 2-bit ops, newest first ---- */
+        uint32_t n_ops = 0;
         if (tid == 0) {
-            uint32_t n_ops = 0, ops_off = 0;
+            uint32_t ops_off = 0;
             if (BT && finished && dist > 0) {
+              if constexpr (!CKPT) {
                 int cd = dist, ck = kt, comp = 0;
                 uint32_t word = 0;
                 while (!(comp == 0 && cd == 0)) {
@@ -527,6 +574,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                 const uint32_t nw = (n_ops + 15u) >> 4;
                 ops_off = atomicAdd(p.ops_pool_head, nw);
                 if (ops_off + nw > p.ops_pool_words) { n_ops = 0; finished = false; }
+              }
             }
             ctl->n_ops = n_ops;
             ctl->ops_off = ops_off;
@@ -546,7 +594,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
             p.out[idx] = r;
         }
         G::sync();
-        if (BT) {
+        if (BT && !CKPT) {
             /* copy the op words from the group's scratch into the pool (coalesced) */
             const uint32_t nw = (ctl->n_ops + 15u) >> 4;
             const uint32_t off = ctl->ops_off;
@@ -558,12 +606,215 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         } else {
             if (tid == 0) {
                 /* single buffer (shared memory is tight): fetch the next pair now */
-                const uint32_t nxt = pop();
+                const uint32_t nxt = pop(0);
                 ctl->idx[0] = nxt;
                 if (nxt != kInvalidIdx) issue_load(0, nxt);
             }
             G::sync();
         }
+    }
+}
+
+/* ======================================================================== */
+/*                 checkpointed traceback (warp per pair)                   */
+/* ======================================================================== */
+/*
+ * Second half of the CKPT path.  The forward kernel left, for every pair, a snapshot of
+ * the ring rows every P = p.ck_period scores (one arena per pair, indexed by queue position).
+ * A warp walks its pair from (distance, k_target) down to (0, 0), segment by segment:
+ * stage the window of snapshot c = P * floor((d-1)/P) under the cell, recompute scores
+ * c+1 .. d on the dependency cone |k - k_apex| <= d_apex - d level by level (same
+ * recurrence, same extend), then follow the path while it stays above c using the
+ * forward tie-breaks on the recomputed offsets (I/D: extend beats open; M: D beats X
+ * beats I).  Emits the same newest-first 2-bit op stream as the decision-byte walk.
+ * Running it as its own kernel puts thousands of these latency-bound walks in flight
+ * instead of one per resident CTA (model: oracle/kernel_model.c, km_align_pair_ckpt).
+ */
+__device__ __forceinline__ int extend_packed_g(const uint32_t *__restrict__ Pw, const uint32_t *__restrict__ Tw,
+                                               int plen, int tlen, int k, int off)
+{
+    const int v = off - k, h = off;
+    const int rem = min(plen - v, tlen - h);
+    if (rem < 0) return kOffNull;
+    int acc = 0;
+    while (acc < rem) {
+        const uint32_t v2 = (uint32_t)(v + acc), h2 = (uint32_t)(h + acc);
+        const uint32_t a = __ldg(Pw + (v2 >> 3)) << ((v2 & 7u) * 2u);
+        const uint32_t b = __ldg(Tw + (h2 >> 3)) << ((h2 & 7u) * 2u);
+        const int nv = 16 - (int)max(v2 & 7u, h2 & 7u);
+        const int eq = min(__clz((int)(a ^ b)) >> 1, nv);
+        acc += eq;
+        if (eq < nv) break;
+    }
+    return off + min(acc, rem);
+}
+
+template <bool ASCII, int P>
+__global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constant__ KernelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    /* Per warp and component: a rectangle of levels -(A-2) .. P (score c + level) by 2P+1
+     * diagonals around the apex; levels <= 0 hold the staged snapshot window. */
+    constexpr int WP = 2 * P + 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NULLV = kOffNull;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = p.x, e = p.e, A = p.A, oe = p.o + p.e;
+    const int L0 = A - 2;                                      /* row of level 0 */
+    const uint32_t comp_bytes = (uint32_t)((P + A - 1) * WP * 2);
+    const uint32_t warp_bytes = (3u * comp_bytes + 15u) & ~15u;
+    const uint32_t sM = smem_u32(smem_raw) + (uint32_t)warp * warp_bytes;
+    const uint32_t sI = sM + comp_bytes, sD = sI + comp_bytes;
+    /* address of (level, k): base + 2 * ((level + L0) * WP + (k - kc + P)) */
+
+    while (true) {
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(p.tb_queue, 1u);
+        pos = __shfl_sync(FULL, pos, 0);
+        if (pos >= p.n_items) break;
+        const uint32_t idx = p.order[pos];
+        const wfagpu_pair_out_t res = p.out[idx];
+        if (!(res.status & WFAGPU_ST_FINISHED) || res.distance <= 0) continue;
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const int plen = (int)pr.plen, tlen = (int)pr.tlen, dist = res.distance;
+        const uint32_t *const Pw = p.packed + pr.p_word;
+        const uint32_t *const Tw = p.packed + pr.t_word;
+        const char *const Pg = p.ascii + pr.p_ascii;
+        const char *const Tg = p.ascii + pr.t_ascii;
+        auto extend = [&](int k, int off) -> int {
+            if (ASCII) return extend_ascii(Pg, Tg, plen, tlen, k, off, NULLV);
+            return extend_packed_g(Pw, Tw, plen, tlen, k, off);
+        };
+        const uint4 *const arena = p.arena + (size_t)pos * p.arena_units;
+        /* op words go straight to the pool: at most 2 ops per score */
+        const uint32_t nw_max = ((2u * (uint32_t)dist + 15u) >> 4) + 1u;
+        uint32_t ops_off = 0;
+        if (lane == 0) ops_off = atomicAdd(p.ops_pool_head, nw_max);
+        ops_off = __shfl_sync(FULL, ops_off, 0);
+        bool tb_ok = (ops_off + nw_max <= p.ops_pool_words);
+        uint32_t *const ops = p.ops_pool + ops_off;
+
+        const int m00 = extend(0, 0);
+        int cd = dist, ck = tlen - plen, comp = 0;
+        uint32_t word = 0, n_ops = 0;
+        while (!(comp == 0 && cd == 0) && tb_ok) {
+            if (cd <= 0) { tb_ok = false; break; }
+            const int c = ((cd - 1) / P) * P, Rr = cd - c, kc = ck;
+            const int jlo = P - Rr, jhi = P + Rr;                  /* columns of the cone's base */
+            /* ---- stage snapshot c as levels 0, -1, ...: M ages 0..A-2, I/D ages 0..e-1 ---- */
+            if (c == 0) {
+                for (int a = 0; a < A - 1; ++a)
+                    for (int j = jlo + lane; j <= jhi; j += 32) {
+                        sts_16(sM + 2u * (uint32_t)((L0 - a) * WP + j), (a == 0 && j == P - kc) ? m00 : NULLV);
+                        if (a < e) {
+                            sts_16(sI + 2u * (uint32_t)((L0 - a) * WP + j), NULLV);
+                            sts_16(sD + 2u * (uint32_t)((L0 - a) * WP + j), NULLV);
+                        }
+                    }
+            } else {
+                const int nc = p.steps[c].n;
+                const int k0 = -((nc + 7) & ~7);
+                const int units = (((nc + 7) & ~7) + ((nc + 8) & ~7)) >> 3;
+                const int16_t *snap = reinterpret_cast<const int16_t *>(arena + p.ck_off[c / P]) - k0;
+                const size_t pitch = (size_t)units * 8;
+                for (int j = jlo + lane; j <= jhi; j += 32) {
+                    const int k = kc - P + j;
+                    const bool in = (k >= -nc && k <= nc);
+                    for (int a = 0; a < A - 1; ++a)
+                        sts_16(sM + 2u * (uint32_t)((L0 - a) * WP + j), in ? (int)__ldcs(snap + (size_t)a * pitch + k) : NULLV);
+                    for (int a = 0; a < e; ++a) {
+                        sts_16(sI + 2u * (uint32_t)((L0 - a) * WP + j), in ? (int)__ldcs(snap + (size_t)(A - 1 + a) * pitch + k) : NULLV);
+                        sts_16(sD + 2u * (uint32_t)((L0 - a) * WP + j), in ? (int)__ldcs(snap + (size_t)(A - 1 + e + a) * pitch + k) : NULLV);
+                    }
+                }
+            }
+            uint32_t my_nk = 0;          /* lane l: half width | kind << 16 of score c + 1 + l */
+            if (lane < Rr) { const wfagpu_step_t t = p.steps[c + 1 + lane]; my_nk = (uint32_t)t.n | ((uint32_t)t.kind << 16); }
+            __syncwarp();
+            /* ---- recompute levels 1 .. Rr on the cone ---- */
+            for (int i = 1; i <= Rr; ++i) {
+                const uint32_t nk = __shfl_sync(FULL, my_nk, i - 1);
+                const int n_i = (int)(nk & 0xffffu), kind_i = (int)(nk >> 16);
+                const int half = Rr - i;
+                const uint32_t rowC = 2u * (uint32_t)((i + L0) * WP);
+                const uint32_t rowX = 2u * (uint32_t)((i - x + L0) * WP);
+                const uint32_t rowO = 2u * (uint32_t)((i - oe + L0) * WP);
+                const uint32_t rowE = 2u * (uint32_t)((i - e + L0) * WP);
+                for (int j = P - half + lane; j <= P + half; j += 32) {
+                    const int k = kc - P + j;
+                    const uint32_t cj = 2u * (uint32_t)j;
+                    int vM = NULLV, vI = NULLV, vD = NULLV;
+                    if (kind_i != WFAGPU_STEP_NULL && k >= -n_i && k <= n_i) {
+                        if (kind_i == WFAGPU_STEP_M) {
+                            vM = lds_s16(sM + rowX + cj) + 1;
+                        } else {
+                            vI = max(lds_s16(sM + rowO + cj - 2u), lds_s16(sI + rowE + cj - 2u)) + 1;
+                            vD = max(lds_s16(sM + rowO + cj + 2u), lds_s16(sD + rowE + cj + 2u));
+                            vM = max(max(lds_s16(sM + rowX + cj) + 1, vD), vI);
+                        }
+                        if (vM >= 0) vM = extend(k, vM);
+                    }
+                    sts_16(sM + rowC + cj, vM);
+                    sts_16(sI + rowC + cj, vI);
+                    sts_16(sD + rowC + cj, vD);
+                }
+                __syncwarp();
+            }
+            /* ---- walk while the path stays above c (uniform across the warp; lane 0 stores) ---- */
+            auto at = [&](uint32_t base, int d2, int k) -> int {
+                return lds_s16(base + 2u * (uint32_t)((d2 - c + L0) * WP + (k - kc + P)));
+            };
+            while (cd > c && !(comp == 0 && cd == 0)) {
+                const uint32_t nk = __shfl_sync(FULL, my_nk, cd - c - 1);
+                const int kind_c = (int)(nk >> 16);
+                uint32_t op;
+                if (comp == 0) {
+                    op = OP_SUB;
+                    if (kind_c == WFAGPU_STEP_M) {
+                        cd -= x;
+                    } else {
+                        const int X = at(sM, cd - x, ck) + 1;
+                        const int I = at(sI, cd, ck), D = at(sD, cd, ck);
+                        if (D >= X && D >= I) comp = 2;          /* D beats X beats I */
+                        else if (X >= I) cd -= x;
+                        else comp = 1;
+                    }
+                } else if (comp == 1) {
+                    op = OP_INS;
+                    const int opn = at(sM, cd - oe, ck - 1), ext = at(sI, cd - e, ck - 1);
+                    ck -= 1;
+                    if (ext >= opn) cd -= e; else { cd -= oe; comp = 0; }   /* extend beats open */
+                } else {
+                    op = OP_DEL;
+                    const int opn = at(sM, cd - oe, ck + 1), ext = at(sD, cd - e, ck + 1);
+                    ck += 1;
+                    if (ext >= opn) cd -= e; else { cd -= oe; comp = 0; }
+                }
+                word |= op << (2 * (n_ops & 15u));
+                ++n_ops;
+                if ((n_ops & 15u) == 0) {
+                    if (lane == 0) ops[(n_ops >> 4) - 1] = word;
+                    word = 0;
+                }
+                if (cd < 0 || (n_ops >> 4) >= nw_max) { tb_ok = false; break; }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            wfagpu_pair_out_t r = res;
+            if (tb_ok) {
+                if (n_ops & 15u) ops[n_ops >> 4] = word;
+                r.ops_off = ops_off;
+                r.n_ops = n_ops;
+            } else {
+                /* cannot happen with a consistent snapshot arena; leave the pair to the re-dispatch loop */
+                r.distance = 0; r.ops_off = 0; r.n_ops = 0;
+                r.status = WFAGPU_ST_OVERBUDGET;
+                p.retry_list[atomicAdd(p.retry_count, 1u)] = idx;
+            }
+            p.out[idx] = r;
+        }
+        __syncwarp();
     }
 }
 
@@ -637,7 +888,7 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
         tma_load_1d(dp, p.packed + pr.p_word, pw * 4u, &ctl->bar[stage]);
         tma_load_1d(dt, p.packed + pr.t_word, tw * 4u, &ctl->bar[stage]);
     };
-    auto pop = [&]() -> uint32_t {
+    auto pop = [&](int slot) -> uint32_t {
         const uint32_t pos = atomicAdd(p.queue, 1u);
         return pos < p.n_items ? p.order[pos] : kInvalidIdx;
     };
@@ -647,7 +898,7 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
             mbar_init(&ctl->bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        const uint32_t first = pop();
+        const uint32_t first = pop(0);
         ctl->idx[0] = first;
         if (first != kInvalidIdx) issue_load(0, first);
     }
@@ -659,7 +910,7 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
         const uint32_t idx = ctl->idx[stage];
         if (idx == kInvalidIdx) break;
         if (tid == 0 && p.stages == 2) {
-            const uint32_t nxt = pop();
+            const uint32_t nxt = pop(stage ^ 1);
             ctl->idx[stage ^ 1] = nxt;
             if (nxt != kInvalidIdx) issue_load(stage ^ 1, nxt);
         }
@@ -886,7 +1137,7 @@ __global__ void __launch_bounds__(1024, 1) wfa_banded_kernel(const __grid_consta
             stage ^= 1;
         } else {
             if (tid == 0) {
-                const uint32_t nxt = pop();
+                const uint32_t nxt = pop(0);
                 ctl->idx[0] = nxt;
                 if (nxt != kInvalidIdx) issue_load(0, nxt);
             }
@@ -1069,20 +1320,20 @@ void launch_cigar_text(const CigarParams &p, cudaStream_t s)
 
 /* ---- host-side launch helpers ---------------------------------------------- */
 
-template <bool WARP, bool ASCII, bool BT, typename R = RingS16>
+template <bool WARP, bool ASCII, bool BT, typename R = RingS16, bool CKPT = false>
 static cudaError_t launch_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
-    auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R>;
+    auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R, CKPT>;
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, threads, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-template <bool WARP, bool ASCII, bool BT, typename R = RingS16>
+template <bool WARP, bool ASCII, bool BT, typename R = RingS16, bool CKPT = false>
 static int occupancy_one(int threads, size_t smem)
 {
-    auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R>;
+    auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R, CKPT>;
     int n = 0;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
@@ -1096,6 +1347,45 @@ size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups
     const size_t seq_bytes = (size_t)seq_words * 4;
     const size_t group_bytes = (ring_bytes + 2 * (size_t)stages * seq_bytes + sizeof(GroupCtl) + 15) & ~(size_t)15;
     return group_bytes * (size_t)groups_per_cta;
+}
+
+size_t traceback_smem_bytes(int A, int period, int warps)
+{
+    const size_t per_warp = ((size_t)3 * (period + A - 1) * (2 * period + 1) * 2 + 15) & ~(size_t)15;
+    return per_warp * (size_t)warps;
+}
+
+using tb_kernel_t = void (*)(const KernelParams);
+static tb_kernel_t traceback_fn(bool ascii, int period)
+{
+    switch (period) {
+    case 8: return ascii ? wfa_traceback_kernel<true, 8> : wfa_traceback_kernel<false, 8>;
+    case 16: return ascii ? wfa_traceback_kernel<true, 16> : wfa_traceback_kernel<false, 16>;
+    case 32: return ascii ? wfa_traceback_kernel<true, 32> : wfa_traceback_kernel<false, 32>;
+    default: return nullptr;
+    }
+}
+
+cudaError_t launch_traceback(const KernelParams &p, int ctas, int warps, bool ascii, cudaStream_t s)
+{
+    const size_t smem = traceback_smem_bytes(p.A, p.ck_period, warps);
+    tb_kernel_t kfn = traceback_fn(ascii, p.ck_period);
+    if (!kfn) return cudaErrorInvalidValue;
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kfn<<<ctas, 32 * warps, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+int traceback_max_ctas_per_sm(int A, int period, int warps, bool ascii)
+{
+    const size_t smem = traceback_smem_bytes(A, period, warps);
+    tb_kernel_t kfn = traceback_fn(ascii, period);
+    int n = 0;
+    if (!kfn) return 0;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, 32 * warps, smem) != cudaSuccess) return 0;
+    return n;
 }
 
 #define WFAGPU_DISPATCH(FN, ...)                                                              \
@@ -1117,6 +1407,12 @@ cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_pe
         return bt ? launch_one<false, false, true, RingG32>(p, threads, ctas, smem_bytes, s)
                   : launch_one<false, false, false, RingG32>(p, threads, ctas, smem_bytes, s);
     }
+    if (p.ck_off) {
+        /* checkpointed traceback (CTA per pair, shared-memory rings, CIGAR wanted) */
+        if (warp || !bt) return cudaErrorInvalidValue;
+        return ascii ? launch_one<false, true, true, RingS16, true>(p, threads, ctas, smem_bytes, s)
+                     : launch_one<false, false, true, RingS16, true>(p, threads, ctas, smem_bytes, s);
+    }
     return WFAGPU_DISPATCH(launch_one, p, threads, ctas, smem_bytes, s);
 }
 
@@ -1128,10 +1424,12 @@ int large_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii, bool bt)
               : occupancy_one<false, false, false, RingG32>(threads, smem_bytes);
 }
 
-int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii, bool bt)
+int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii, bool bt, bool ckpt)
 {
     const bool warp = (group_threads == 32);
     const int threads = warp ? 32 * groups_per_cta : group_threads;
+    if (ckpt) return ascii ? occupancy_one<false, true, true, RingS16, true>(threads, smem_bytes)
+                           : occupancy_one<false, false, true, RingS16, true>(threads, smem_bytes);
     return WFAGPU_DISPATCH(occupancy_one, threads, smem_bytes);
 }
 

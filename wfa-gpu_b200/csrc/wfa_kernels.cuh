@@ -37,6 +37,7 @@ struct KernelParams {
     const uint32_t *order;        /* pair indices, longest first                             */
     uint32_t n_items;             /* entries of `order`                                      */
     uint32_t *queue;              /* atomic work-queue head                                  */
+    uint32_t *tb_queue;           /* same for the traceback kernel                           */
     const wfagpu_step_t *steps;
     int d_end;                    /* scores 1 .. d_end-1 may be computed                     */
     int n_cap;                    /* largest half width the rings of this launch can hold    */
@@ -56,6 +57,9 @@ struct KernelParams {
     uint64_t gring_elems;         /* int32 elements per group                                */
     uint4 *arena;
     uint64_t arena_units;         /* uint4 units per group                                   */
+    const uint32_t *ck_off;       /* checkpointed traceback: arena offset (units) of the snapshot of
+                                   * score j * ck_period; null = one decision byte per cell  */
+    int ck_period;                /* 8, 16 or 32                                              */
     uint32_t *ops_scratch;        /* per-group scratch for the traceback's op words          */
     uint32_t ops_scratch_words;
     /* outputs */
@@ -97,12 +101,17 @@ void launch_cigar_text(const CigarParams &p, cudaStream_t s);
 /* group_threads == 32 -> warp-per-pair variant; otherwise CTA-per-pair */
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
                          size_t smem_bytes, bool ascii_extend, cudaStream_t s);
+/* traceback of the checkpointed path: `warps` pairs per CTA */
+cudaError_t launch_traceback(const KernelParams &p, int ctas, int warps, bool ascii_extend, cudaStream_t s);
+size_t traceback_smem_bytes(int A, int period, int warps);
+int traceback_max_ctas_per_sm(int A, int period, int warps, bool ascii_extend);
 size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages);
 cudaError_t launch_banded(const KernelParams &p, int threads, int ctas, size_t smem_bytes, bool ascii_extend,
                           cudaStream_t s);
 size_t banded_smem_bytes(int A, int win, int seq_words, int stages);
 int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii_extend, bool with_bt);
 int large_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii_extend, bool with_bt);
-int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend, bool with_bt);
+int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend, bool with_bt,
+                          bool ckpt = false);
 
 } // namespace wfagpu
