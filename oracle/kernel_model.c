@@ -82,6 +82,7 @@ static int km_extend(const char *text, const char *pattern, int tlen, int plen, 
 }
 
 static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
 
 /*
  * One pair.  ops_out receives the 2-bit ops NEWEST FIRST (traceback order),
@@ -233,19 +234,46 @@ typedef struct {
     const char *pattern, *text;
     int plen, tlen;
     int16_t m00; /* M[0][0] */
+    int kt, dmax; /* score-bound pruning (dmax < 0: off) */
 } km_tb_t;
+
+/* Score-bound pruning: when the pair is known to finish with a score <= dmax, a cell (d, k) can
+ * only lie on an alignment of that score if d + e * |k - kt| <= dmax (every diagonal between k and
+ * the target diagonal kt costs at least one gap extension).  Cells outside are never computed and
+ * read as NULL.  Every complete path through a pruned cell scores more than dmax, so the cells of
+ * the optimal path the reference backtraces keep their values and win the same tie-breaks:
+ * identical score and CIGAR for every pair that finishes within dmax. */
+static void km_prune_range(int d, int n, int kt, int dmax, int e, int *lo, int *hi)
+{
+    *lo = -n; *hi = n;
+    if (dmax < 0) return;
+    if (d > dmax) { *lo = 1; *hi = 0; return; }
+    const int g = (dmax - d) / e;
+    if (kt - g > *lo) *lo = kt - g;
+    if (kt + g < *hi) *hi = kt + g;
+}
 
 static int km_in_range(const km_tb_t *t, int d, int k)
 {
     if (d < 0) return 0;
-    const int n = t->tab[d].n;
-    return k >= -n && k <= n;
+    int lo, hi;
+    km_prune_range(d, t->tab[d].n, t->kt, t->dmax, t->e, &lo, &hi);
+    return k >= lo && k <= hi;
 }
 
 /* offset of component comp (0 M, 1 I, 2 D) at (d, k) as the forward pass saw it */
 static int km_tb_get(const km_tb_t *t, int comp, int d, int k)
 {
-    if (d < 0 || !km_in_range(t, d, k)) return KM_NULL;
+    if (d > t->c && !km_in_range(t, d, k)) return KM_NULL;
+    if (d <= t->c && t->c > 0) {
+        /* snapshot rows are masked with ONE window, that of score c widened by a cell (what the
+         * GPU traceback does); inside it older rows hold values, guard NULLs -- never stale cells */
+        int lo, hi;
+        const int nc = t->tab[t->c].n;
+        km_prune_range(t->c, nc, t->kt, t->dmax, t->e, &lo, &hi);
+        if (t->dmax >= 0) { lo = imax(-nc, lo - 1); hi = imin(nc, hi + 1); }
+        if (k < lo || k > hi) return KM_NULL;
+    }
     if (d > t->c) {
         const int i = d - t->c;
         if (k < t->klo || k > t->khi) return KM_NULL; /* outside the cone: never needed */
@@ -264,7 +292,7 @@ static int km_tb_get(const km_tb_t *t, int comp, int d, int k)
 }
 
 int km_align_pair_ckpt(const char *pattern, int plen, const char *text, int tlen,
-                       int x, int o, int e, const km_step_t *tab, int d_end, int n_cap, int period,
+                       int x, int o, int e, const km_step_t *tab, int d_end, int n_cap, int period, int dmax,
                        int *finished, int *distance, uint8_t *ops_out, int ops_cap, int *n_ops, long *recomputed)
 {
     const int A = imax(o + e, x) + 1, E1 = e + 1, G = A;
@@ -295,10 +323,13 @@ int km_align_pair_ckpt(const char *pattern, int plen, const char *text, int tlen
             if (st.kind == KM_KIND_NULL) {
                 for (int k = -n - G; k <= n + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
             } else if (st.kind == KM_KIND_M) {
-                const int16_t *Mx = Mr + ((d - x) % A) * W + C;
-                for (int k = -n - G; k <= n + G; k++) {
+                const int16_t *Mx = Mr + ((((d - x) % A) + A) % A) * W + C;
+                int lo, hi;
+                km_prune_range(d, n, kt, dmax, e, &lo, &hi);
+                if (dmax >= 0) for (int k = -n - G; k <= n + G; k++) { Mc[k] = 12345; Ic[k] = 12345; Dc[k] = 12345; } /* poison */
+                for (int k = lo - G; k <= hi + G; k++) {
                     Ic[k] = KM_NULL; Dc[k] = KM_NULL;
-                    if (k < -n || k > n) { Mc[k] = KM_NULL; continue; }
+                    if (k < lo || k > hi) { Mc[k] = KM_NULL; continue; }
                     int m = Mx[k] + 1;
                     if (m >= 0) m = km_extend(text, pattern, tlen, plen, k, m);
                     Mc[k] = (int16_t)m;
@@ -308,9 +339,12 @@ int km_align_pair_ckpt(const char *pattern, int plen, const char *text, int tlen
                 const int16_t *Ie = Ir + ((((d - e) % E1) + E1) % E1) * W + C;
                 const int16_t *De = Dr + ((((d - e) % E1) + E1) % E1) * W + C;
                 const int16_t *Mxx = Mr + ((((d - x) % A) + A) % A) * W + C;
-                for (int k = -n - G; k < -n; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
-                for (int k = n + 1; k <= n + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
-                for (int k = -n; k <= n; k++) {
+                int lo, hi;
+                km_prune_range(d, n, kt, dmax, e, &lo, &hi);
+                if (dmax >= 0) for (int k = -n - G; k <= n + G; k++) { Mc[k] = 12345; Ic[k] = 12345; Dc[k] = 12345; } /* poison */
+                for (int k = lo - G; k < lo; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+                for (int k = hi + 1; k <= hi + G; k++) { Mc[k] = KM_NULL; Ic[k] = KM_NULL; Dc[k] = KM_NULL; }
+                for (int k = lo; k <= hi; k++) {
                     const int I = imax(Mo[k - 1] + 1, Ie[k - 1] + 1);
                     const int D = imax(Mo[k + 1], De[k + 1]);
                     int M = imax(imax(Mxx[k] + 1, D), I);
@@ -345,7 +379,7 @@ int km_align_pair_ckpt(const char *pattern, int plen, const char *text, int tlen
         memset(&t, 0, sizeof(t));
         t.A = A; t.E1 = E1; t.W = W; t.C = C; t.P = P; t.tab = tab; t.x = x; t.o = o; t.e = e;
         t.ckM = ckM; t.ckI = ckI; t.ckD = ckD; t.pattern = pattern; t.text = text; t.plen = plen; t.tlen = tlen;
-        t.m00 = m00;
+        t.m00 = m00; t.kt = kt; t.dmax = dmax;
         const int SW = 2 * P + 3;
         t.sM = (int16_t *)malloc((size_t)(P + 2) * SW * sizeof(int16_t));
         t.sI = (int16_t *)malloc((size_t)(P + 2) * SW * sizeof(int16_t));

@@ -59,7 +59,7 @@ class Oracle:
             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]
         L.km_build_steps.argtypes = [C.c_int] * 5 + [C.POINTER(KmStep), C.POINTER(C.c_uint64)]
         L.km_align_pair_ckpt.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 3 + [
-            C.POINTER(KmStep), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+            C.POINTER(KmStep), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
             C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_long)]
         L.km_align_pair.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 3 + [
             C.POINTER(KmStep), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -114,7 +114,7 @@ class Oracle:
         self.L.orc_free(out)
         return s
 
-    def model_align_ckpt(self, pattern, text, x, o, e, max_steps, period=32):
+    def model_align_ckpt(self, pattern, text, x, o, e, max_steps, period=32, dmax=-1):
         """CPU model of the checkpointed traceback (ring snapshots every `period` scores +
         recomputation on the dependency cone)."""
         p, t = _b(pattern), _b(text)
@@ -125,7 +125,7 @@ class Oracle:
         fin, dist, nops, rec = C.c_int(), C.c_int(), C.c_int(), C.c_long()
         cap = 2 * d_end + 16
         ops = (C.c_uint8 * cap)()
-        rc = self.L.km_align_pair_ckpt(p, len(p), t, len(t), x, o, e, tab, d_end, max_steps, period,
+        rc = self.L.km_align_pair_ckpt(p, len(p), t, len(t), x, o, e, tab, d_end, max_steps, period, dmax,
                                        C.byref(fin), C.byref(dist), ops, cap, C.byref(nops), C.byref(rec))
         assert rc == 0, "checkpointed traceback failed"
         cg = None

@@ -32,6 +32,27 @@ def test_checkpointed_traceback_equals_oracle(oracle, pen, period):
         assert (m["finished"], m["distance"], m["cigar"]) == (r["finished"], r["distance"], r["cigar"])
 
 
+@pytest.mark.parametrize("pen", PENS + [(1, 0, 1), (3, 5, 2), (7, 11, 3), (2, 24, 9)])
+def test_score_bound_pruning_is_exact(oracle, pen):
+    # Cells with d + e*|k - k_target| > dmax are never computed (the model poisons them, so a read of
+    # one would corrupt the result): every pair that finishes with score s <= dmax must come out with
+    # the reference's score and CIGAR, down to the tightest bound dmax = s; and with dmax = s - 1 it
+    # must not finish at all (the GPU re-dispatches it with a larger budget).
+    pairs = make_pairs(11, [(150, 0.05, 12), (700, 0.1, 3), (25, 0.35, 20), (300, 0.2, 4)])
+    pairs += [("", "ACGT"), ("ACGT", ""), ("ACGT", "ACGT"), ("A", "C"), ("ACGTACGTAC", "TTTTTTTTTT"),
+              ("ACGT" * 30, "ACGT" * 30 + "T" * 20), ("GATTACA" * 20 + "C" * 37, "GATTACA" * 20)]
+    for p, t in pairs:
+        r = oracle.align(p, t, *pen, 1200)
+        assert r["finished"]
+        s = r["distance"]
+        for dmax in (s, s + 1, s + 3, int(1.2 * s) + 2, 3 * s + 7):
+            for period in (7, 16):
+                m = oracle.model_align_ckpt(p, t, *pen, 1200, period, dmax)
+                assert (m["finished"], m["distance"], m["cigar"]) == (True, s, r["cigar"])
+        if s > 0:
+            assert not oracle.model_align_ckpt(p, t, *pen, 1200, 16, s - 1)["finished"]
+
+
 @pytest.mark.parametrize("pen", [(2, 3, 1), (4, 6, 2), (5, 3, 2)])
 def test_model_budget_rule_equals_oracle(oracle, pen):
     # which pairs are over budget must match the reference rule (steps < max_steps - 1)

@@ -135,6 +135,7 @@ struct Slot {
     size_t ascii_bytes = 0;
     size_t packed_words = 0;
     uint32_t max_len = 0;
+    uint32_t kt_max = 0;               /* largest |tlen - plen| of the batch */
     wfagpu_plan_t plan{};
     wfagpu_batch_stats_t stats{};
     bool have_events = false;
@@ -259,11 +260,12 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
     if (s.h_pairs.ensure(n) || s.h_order.ensure(n)) return -1;
     /* packed layout + longest-first schedule */
     size_t words = 0;
-    uint32_t max_len = 0;
+    uint32_t max_len = 0, kt_max = 0;
     uint64_t min_sum = ~0ull, max_sum = 0;
     for (size_t i = 0; i < n; ++i) {
         wfagpu_pair_t p = pairs[i];
         const uint64_t sum = (uint64_t)p.plen + p.tlen;
+        kt_max = std::max(kt_max, p.plen > p.tlen ? p.plen - p.tlen : p.tlen - p.plen);
         min_sum = std::min(min_sum, sum);
         max_sum = std::max(max_sum, sum);
         p.p_word = (uint32_t)words;
@@ -281,6 +283,7 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
     }
     s.packed_words = words;
     s.max_len = max_len;
+    s.kt_max = kt_max;
     if ((uint64_t)min_sum * 8 < (uint64_t)max_sum * 7) {
         /* longest first only pays when the lengths differ by more than ~12 %: for uniform
          * reads the queue order is irrelevant and the sort would dominate the host time */
@@ -489,13 +492,30 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     const int d_full = s.tab_d_end;
     int n_full = 0;
     for (int dd = d_full - 1; dd >= 0 && dd >= d_full - 4; --dd) n_full = std::max(n_full, (int)tab[dd].n);
-    /* half width to provision: the full budget, or (first pass only) what recent batches
-     * with these penalties needed plus a margin -- pairs that outgrow it are re-dispatched */
-    int n_want = n_full;
-    if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e) {
-        const long long dh = std::min<long long>((long long)d->hint_dist + d->hint_dist / 12 + 8, d_full - 1);
-        n_want = std::min(n_full, (int)tab[dh].n + 4);
-    }
+    /* Scores to provision for: the full budget, or (first pass only) what recent batches with
+     * these penalties needed plus a margin -- pairs that outgrow it are re-dispatched.  The kernel
+     * prunes every cell that cannot reach the target diagonal within d_end - 1 (score-bound
+     * pruning), so the rings only have to hold max_d min(n_d, kt_max + (d_end - 1 - d) / e). */
+    int d_want = d_full;
+    if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e)
+        d_want = (int)std::min<long long>((long long)d->hint_dist + d->hint_dist / 12 + 8, d_full - 1) + 1;
+    const int pen_e = plan.e;
+    const long long kt_max = s.kt_max;
+    auto n_need = [&](int d_end) -> int {
+        /* n_d grows, kt + (Dmax - d) / e shrinks: the largest min sits where they cross */
+        const long long Dmax = d_end - 1;
+        const long long ktm = std::min<long long>(kt_max, Dmax / pen_e);
+        int lo = 0, hi = d_end;                      /* first d with n_d >= ktm + (Dmax - d) / e */
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if ((long long)tab[mid].n >= ktm + (Dmax - mid) / pen_e) hi = mid; else lo = mid + 1;
+        }
+        long long best = 1;
+        for (int dd = std::max(0, lo - 2); dd < std::min(d_end, lo + 3); ++dd)
+            best = std::max(best, std::min<long long>(tab[dd].n, ktm + (Dmax - dd) / pen_e));
+        return (int)best;
+    };
+    int n_want = plan.band > 0 ? n_full : n_need(d_want);
     const bool banded = plan.band > 0;
     LaunchCfg c{};
     int rc = 0;
@@ -530,18 +550,21 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     }
     if (rc) return rc;
     /* scores this launch can reach and the decision units they need */
-    int d_end = d_full;
+    int d_end = banded ? d_full : d_want;
     uint64_t arena_units = s.tab_arena_units;
-    if (!banded && c.n_cap < n_full) {
-        int lo = 0, hi = d_full;                     /* first score whose half width exceeds n_cap */
-        while (lo < hi) {
-            const int mid = (lo + hi) / 2;
-            if ((int)tab[mid].n > c.n_cap) hi = mid; else lo = mid + 1;
+    if (!banded) {
+        if (c.n_cap < n_want) {
+            int lo = 1, hi = d_want;                 /* largest d_end whose pruned wavefronts fit the rings */
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) / 2;
+                if (n_need(mid) <= c.n_cap) lo = mid; else hi = mid - 1;
+            }
+            d_end = lo;
         }
-        d_end = lo;
         arena_units = d_end < d_full ? tab[d_end].row_off : s.tab_arena_units;
     }
-    *capped_out = c.n_cap < n_full;
+    *capped_out = d_end < d_full;
+
     /* memory budget of the arenas: a third of the free device memory */
     size_t arena_budget = 0;
     {
@@ -554,7 +577,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         /* Snapshot period: the traceback recomputes ~ score * P cells per pair against ~ score^2 in
          * the forward pass, the snapshots take ~ 1/P of the cells: short periods for low scores,
          * longer ones when memory is tight. */
-        const int d_expect = (n_want < n_full) ? std::min(d_end, d->hint_dist + 1) : d_end;
+        const int d_expect = (d_want < d_full) ? std::min(d_end, d->hint_dist + 1) : d_end;
         period = d->force_period ? d->force_period : (d_expect >= 3000 ? 32 : 16);   /* measured on B200: 8 never wins */
         for (;;) {
             if (ensure_ck_table(s, plan, period)) return -1;

@@ -267,6 +267,19 @@ __device__ __forceinline__ int extend_ascii(const char *__restrict__ P, const ch
     return off + acc;
 }
 
+/* Score-bound pruning window of one score: the diagonals of [-n, n] within q = (Dmax - d) / e of
+ * the target diagonal.  When none is (an all-NULL step) the window is the clamped full range, so
+ * that the rows still read as NULL wherever a later score may look.  Returns whether any cell is
+ * computed.  Used identically by the forward pass and by the checkpointed traceback. */
+__device__ __forceinline__ bool prune_window(int n, int kt, int q, int n_cap, int &lo, int &hi)
+{
+    lo = max(-n, kt - q);
+    hi = min(n, kt + q);
+    const bool live = lo <= hi;
+    if (!live) { hi = min(n, n_cap); lo = -hi; }
+    return live;
+}
+
 struct GroupCtl {
     uint64_t bar[2];     /* TMA completion barriers, one per sequence stage */
     uint32_t idx[2];     /* pair index staged in each buffer                */
@@ -418,37 +431,49 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                 RA aDe = R::add(D0, (uint32_t)((E1 - e % E1) % E1) * row_bytes);
                 int ck_left = p.ck_period, ck_j = 0;
                 /* snapshot of the ring rows the scores above d can still read: M of scores d .. d-A+2,
-                 * I and D of d .. d-e+1, each over [-n, n] rounded out to 16-byte units */
-                auto checkpoint = [&](int n) {
+                 * I and D of d .. d-e+1.  A snapshot row covers [-n, n] rounded out to 16-byte units;
+                 * only the units of [lo - 1, hi + 1] (all that later scores can read) are copied. */
+                auto checkpoint = [&](int n, int lo, int hi) {
                     if constexpr (CKPT) {
-                        const int k0 = -((n + 7) & ~7);
-                        const int units = (((n + 7) & ~7) + ((n + 8) & ~7)) >> 3;
-                        uint4 *dst = arena + p.ck_off[ck_j];
+                        const int pitch = (((n + 7) & ~7) + ((n + 8) & ~7)) >> 3;       /* units per snapshot row */
+                        const int k0 = max((lo - 1) & ~7, -((n + 7) & ~7));               /* floor to 8 diagonals   */
+                        const int units = ((min((hi + 1) | 7, ((n + 8) & ~7) - 1) - k0) + 1) >> 3;
+                        uint4 *dst = arena + p.ck_off[ck_j] + ((k0 + ((n + 7) & ~7)) >> 3);
                         uint32_t row = (uint32_t)aMc;
                         for (int a = 0; a < A - 1; ++a) {
                             for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
-                            dst += units;
+                            dst += pitch;
                             row = (row == (uint32_t)M0) ? (uint32_t)Mend - row_bytes : row - row_bytes;
                         }
                         row = (uint32_t)aIc;
                         for (int a = 0; a < e; ++a) {
                             for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
-                            dst += units;
+                            dst += pitch;
                             row = (row == (uint32_t)I0) ? (uint32_t)Iend - row_bytes : row - row_bytes;
                         }
                         row = (uint32_t)aDc;
                         for (int a = 0; a < e; ++a) {
                             for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
-                            dst += units;
+                            dst += pitch;
                             row = (row == (uint32_t)D0) ? (uint32_t)Dend - row_bytes : row - row_bytes;
                         }
                     }
                 };
+                /* Score-bound pruning: this launch only reports pairs that finish with a score
+                 * <= Dmax = d_end - 1, and every diagonal between k and the target diagonal kt costs
+                 * at least one gap extension, so a cell (d, k) with d + e * |k - kt| > Dmax cannot be
+                 * on such an alignment.  Those cells are not computed and read as NULL; the cells of
+                 * the optimal path keep their offsets and win the same tie-breaks (proof and
+                 * poisoned-cell model: oracle/kernel_model.c, km_prune_range).  (Dmax - d) = q*e + r. */
+                int pr_q = (p.d_end - 1) / e, pr_r = (p.d_end - 1) % e;
                 for (int d = 1; d < p.d_end; ++d) {
                     const wfagpu_step_t st = st_next;
                     if (d + 1 < p.d_end) st_next = p.steps[d + 1];
                     const int n = st.n;
-                    if (n > p.n_cap) break;
+                    if (pr_r == 0) { pr_r = e - 1; --pr_q; } else --pr_r;
+                    int lo, hi;
+                    const bool live = prune_window(n, kt, pr_q, p.n_cap, lo, hi);
+                    if (live && (lo < -p.n_cap || hi > p.n_cap)) break;     /* wider than the rings of this launch */
                     aMc = R::add(aMc, row_bytes); if (aMc == Mend) aMc = M0;
                     aMx = R::add(aMx, row_bytes); if (aMx == Mend) aMx = M0;
                     aMo = R::add(aMo, row_bytes); if (aMo == Mend) aMo = M0;
@@ -457,41 +482,39 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                     aDc = R::add(aDc, row_bytes); if (aDc == Dend) aDc = D0;
                     aDe = R::add(aDe, row_bytes); if (aDe == Dend) aDe = D0;
 
-                    if (st.kind == WFAGPU_STEP_NULL) {
-                        for (int k = -n - GW + tid; k <= n + GW; k += gsz) {
+                    if (st.kind == WFAGPU_STEP_NULL || !live) {
+                        for (int k = lo - GW + tid; k <= hi + GW; k += gsz) {
                             R::st(aMc, k, NULLV);
                             R::st(aIc, k, NULLV);
                             R::st(aDc, k, NULLV);
                         }
                         G::sync();
-                        if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n); }
+                        if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n, lo, hi); }
                         continue;
                     }
                     if (st.kind == WFAGPU_STEP_M) {
-                        for (int k = -n - GW + tid; k <= n + GW; k += gsz) {
+                        for (int k = lo - GW + tid; k <= hi + GW; k += gsz) {
                             R::st(aIc, k, NULLV);
                             R::st(aDc, k, NULLV);
                             int m = NULLV;
-                            if (k >= -n && k <= n) {
+                            if (k >= lo && k <= hi) {
                                 m = R::ld(aMx, k) + 1;
                                 if (m >= 0) m = extend(k, m);
                             }
                             R::st(aMc, k, m);
                         }
                     } else {
-                        /* guard cells: NULL on both sides of [-n, n] */
+                        /* guard cells: NULL on both sides of [lo, hi] */
                         for (int g = tid; g < 2 * GW; g += gsz) {
-                            const int k = (g < GW) ? (-n - 1 - g) : (n + 1 + (g - GW));
+                            const int k = (g < GW) ? (lo - 1 - g) : (hi + 1 + (g - GW));
                             R::st(aMc, k, NULLV);
                             R::st(aIc, k, NULLV);
                             R::st(aDc, k, NULLV);
                         }
-                        const int width = 2 * n + 1;
                         /* one decision byte per cell: bit0 I extends, bit1 D extends, bits 3:2 the winner of M
                          * (1 = I, 2 = X, 3 = D); a warp writes 32 consecutive bytes of the pair's row */
-                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + st.row_off);
-                        for (int idc = tid; idc < width; idc += gsz) {
-                            const int k = idc - n;
+                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + st.row_off) + n;
+                        for (int k = lo + tid; k <= hi; k += gsz) {
                             const int io = R::ld(aMo, k - 1) + 1;
                             const int ie = R::ld(aIe, k - 1) + 1;
                             const int dopen = R::ld(aMo, k + 1);
@@ -510,16 +533,16 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                             R::st(aIc, k, I);
                             R::st(aDc, k, D);
                             R::st(aMc, k, M);
-                            if (BT && !CKPT) rowb[idc] = (uint8_t)((bI ? 1u : 0u) | (bD ? 2u : 0u) | (bM0 ? 4u : 0u) | (bM1 ? 8u : 0u));
+                            if (BT && !CKPT) rowb[k] = (uint8_t)((bI ? 1u : 0u) | (bD ? 2u : 0u) | (bM0 ? 4u : 0u) | (bM1 ? 8u : 0u));
                         }
                     }
                     G::sync();
-                    if (kt >= -n && kt <= n && R::ld(aMc, kt) == tlen) {
+                    if (kt >= lo && kt <= hi && R::ld(aMc, kt) == tlen) {
                         finished = true;
                         dist = d;
                         break;
                     }
-                    if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n); }
+                    if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n, lo, hi); }
                 }
             }
         }
@@ -695,7 +718,8 @@ __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constan
         uint32_t *const ops = p.ops_pool + ops_off;
 
         const int m00 = extend(0, 0);
-        int cd = dist, ck = tlen - plen, comp = 0;
+        const int kt = tlen - plen, Dmax = p.d_end - 1;        /* same pruning window as the forward pass */
+        int cd = dist, ck = kt, comp = 0;
         uint32_t word = 0, n_ops = 0;
         while (!(comp == 0 && cd == 0) && tb_ok) {
             if (cd <= 0) { tb_ok = false; break; }
@@ -713,13 +737,17 @@ __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constan
                     }
             } else {
                 const int nc = p.steps[c].n;
+                int wlo, whi;
+                prune_window(nc, kt, (Dmax - c) / e, p.n_cap, wlo, whi);
+                wlo = max(-nc, wlo - 1);
+                whi = min(nc, whi + 1);
                 const int k0 = -((nc + 7) & ~7);
                 const int units = (((nc + 7) & ~7) + ((nc + 8) & ~7)) >> 3;
                 const int16_t *snap = reinterpret_cast<const int16_t *>(arena + p.ck_off[c / P]) - k0;
                 const size_t pitch = (size_t)units * 8;
                 for (int j = jlo + lane; j <= jhi; j += 32) {
                     const int k = kc - P + j;
-                    const bool in = (k >= -nc && k <= nc);
+                    const bool in = (k >= wlo && k <= whi);
                     for (int a = 0; a < A - 1; ++a)
                         sts_16(sM + 2u * (uint32_t)((L0 - a) * WP + j), in ? (int)__ldcs(snap + (size_t)a * pitch + k) : NULLV);
                     for (int a = 0; a < e; ++a) {
@@ -736,6 +764,8 @@ __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constan
                 const uint32_t nk = __shfl_sync(FULL, my_nk, i - 1);
                 const int n_i = (int)(nk & 0xffffu), kind_i = (int)(nk >> 16);
                 const int half = Rr - i;
+                int lo_i, hi_i;
+                if (!prune_window(n_i, kt, (Dmax - (c + i)) / e, p.n_cap, lo_i, hi_i)) { lo_i = 1; hi_i = 0; }
                 const uint32_t rowC = 2u * (uint32_t)((i + L0) * WP);
                 const uint32_t rowX = 2u * (uint32_t)((i - x + L0) * WP);
                 const uint32_t rowO = 2u * (uint32_t)((i - oe + L0) * WP);
@@ -744,7 +774,7 @@ __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constan
                     const int k = kc - P + j;
                     const uint32_t cj = 2u * (uint32_t)j;
                     int vM = NULLV, vI = NULLV, vD = NULLV;
-                    if (kind_i != WFAGPU_STEP_NULL && k >= -n_i && k <= n_i) {
+                    if (kind_i != WFAGPU_STEP_NULL && k >= lo_i && k <= hi_i) {
                         if (kind_i == WFAGPU_STEP_M) {
                             vM = lds_s16(sM + rowX + cj) + 1;
                         } else {
