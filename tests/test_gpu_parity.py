@@ -1,5 +1,7 @@
 """GPU parity: the CUDA path through the public C API vs the oracle (bit-exact
 scores and CIGAR text).  Needs a B200; run with -m gpu."""
+import os
+
 import pytest
 
 import wfagpu
@@ -143,3 +145,16 @@ def test_host_and_device_cigar_text_agree(oracle, monkeypatch):
     assert a.errors() == b.errors()
     assert a.cigars() == b.cigars()
     assert launches_dev > launches_host
+
+
+@pytest.mark.parametrize("variant", [{"WFAGPU_FORCE_BOUND": "1"}, {"WFAGPU_NO_BOUND": "1"}, {"WFAGPU_NO_CKPT": "1"},
+                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_CK_PERIOD": "7"},
+                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_CK_PERIOD": "31"},
+                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_NO_HINT": "1"}])
+def test_kernel_variants_are_bit_exact(variant):
+    # per-pair score bounds on/off, ring snapshots vs decision bytes, snapshot periods: one result
+    import subprocess, sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pr = subprocess.run([_sys.executable, os.path.join(root, "tests", "variant_check.py")], env=dict(os.environ, **variant),
+                        capture_output=True, text=True, timeout=1500)
+    assert pr.returncode == 0, pr.stdout[-3000:] + pr.stderr[-3000:]

@@ -79,7 +79,7 @@ struct PinBuf {
     }
 };
 
-enum { CTR_QUEUE = 0, CTR_POOL = 1, CTR_RETRY = 2, CTR_ASCII = 3, CTR_TBQ = 4, CTR_WORDS = 8 };
+enum { CTR_QUEUE = 0, CTR_POOL = 1, CTR_RETRY = 2, CTR_ASCII = 3, CTR_TBQ = 4, CTR_BQ = 5, CTR_WORDS = 8 };
 
 struct LaunchCfg {
     int group_threads;   /* 32 = warp per pair */
@@ -117,6 +117,7 @@ struct Slot {
     PinBuf<wfagpu_cigar_ref_t> h_refs;
     PinBuf<unsigned long long> h_heads;
     DevBuf<wfagpu_step_t> steps;
+    DevBuf<int32_t> bound;             /* per pair: score upper bound for the pruning */
     DevBuf<uint32_t> ck_off;           /* arena offset of every ring snapshot (checkpointed traceback) */
     std::vector<uint64_t> h_ck_off;    /* [j] = units used by the snapshots of scores < j * period */
     PinBuf<uint32_t> h_ck32;
@@ -152,10 +153,11 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
-    bool no_ckpt = false;
+    bool no_ckpt = false, no_bound = false, force_bound = false;
     int force_period = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
     int hint_dist = 0;
+    double hint_mean = 0;              /* mean score of the finished pairs of that batch */
     int hint_key[3] = {-1, -1, -1};
     bool use_hint = true;
     bool force_large = false;
@@ -212,8 +214,10 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->force_ctas_per_sm = env_int("WFAGPU_CTAS_PER_SM", 0);
     d->force_warp = env_int("WFAGPU_WARP_KERNEL", -1);
     d->no_ckpt = env_int("WFAGPU_NO_CKPT", 0) != 0;
+    d->no_bound = env_int("WFAGPU_NO_BOUND", 0) != 0;
+    d->force_bound = env_int("WFAGPU_FORCE_BOUND", 0) != 0;
     d->force_period = env_int("WFAGPU_CK_PERIOD", 0);
-    if (d->force_period != 8 && d->force_period != 16 && d->force_period != 32) d->force_period = 0;
+    if (d->force_period != 7 && d->force_period != 15 && d->force_period != 31) d->force_period = 0;
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
     d->force_large = env_int("WFAGPU_FORCE_LARGE", 0) != 0;
     d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;
@@ -230,7 +234,7 @@ extern "C" void wfagpu_device_close_all(void)
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.ascii.release(); s.packed.release(); s.pairs.release(); s.order.release();
             s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
-            s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release(); s.ck_off.release(); s.h_ck32.release();
+            s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release(); s.bound.release(); s.ck_off.release(); s.h_ck32.release();
             s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release(); s.slots.release(); s.text.release(); s.refs.release(); s.heads.release();
             s.h_text.release(); s.h_refs.release(); s.h_heads.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
@@ -405,7 +409,8 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
         c->center = ctr(n_cap);
         c->smem = smem;
         /* about 1152 threads per SM in total, never more threads than half the widest wavefront */
-        int t = best_k == 1 ? 1024 : (best_k == 2 ? 512 : ((1152 / best_k) / 32) * 32);
+        /* (measured on B200: 3 x 384, 5 x 192 -- the per-score overhead is paid per warp) */
+        int t = best_k == 1 ? 1024 : (best_k == 2 ? 512 : (best_k == 3 ? 384 : ((960 / best_k) / 32) * 32));
         const int width = 2 * n_cap + 1;
         while (t > 64 && t * 2 > width) t -= 32;
         t = std::max(64, t);
@@ -430,9 +435,16 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
 static void learn_hint(wfagpu_device *d, Slot &s, size_t n)
 {
     int dmax = 0;
+    double sum = 0;
+    size_t cnt = 0;
     for (size_t i = 0; i < n; ++i)
-        if (s.h_out.p[i].status & WFAGPU_ST_FINISHED) dmax = std::max(dmax, s.h_out.p[i].distance);
+        if (s.h_out.p[i].status & WFAGPU_ST_FINISHED) {
+            dmax = std::max(dmax, s.h_out.p[i].distance);
+            sum += s.h_out.p[i].distance;
+            ++cnt;
+        }
     d->hint_dist = d->use_hint ? dmax : 0;
+    d->hint_mean = cnt ? sum / (double)cnt : 0;
     d->hint_key[0] = s.plan.x; d->hint_key[1] = s.plan.o; d->hint_key[2] = s.plan.e;
 }
 
@@ -578,12 +590,12 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
          * the forward pass, the snapshots take ~ 1/P of the cells: short periods for low scores,
          * longer ones when memory is tight. */
         const int d_expect = (d_want < d_full) ? std::min(d_end, d->hint_dist + 1) : d_end;
-        period = d->force_period ? d->force_period : (d_expect >= 3000 ? 32 : 16);   /* measured on B200: 8 never wins */
+        period = d->force_period ? d->force_period : (d_expect >= 3000 ? 31 : 15);   /* measured on B200: shorter never wins */
         for (;;) {
             if (ensure_ck_table(s, plan, period)) return -1;
             arena_units = s.h_ck_off[(size_t)(d_end - 1) / period + 1];      /* snapshots of scores j * P < d_end */
-            if (period >= 32 || d->force_period || (arena_units * sizeof(uint4) + 1) * n_items <= arena_budget) break;
-            period *= 2;
+            if (period >= 31 || d->force_period || (arena_units * sizeof(uint4) + 1) * n_items <= arena_budget) break;
+            period = 2 * period + 1;
         }
         if (arena_units >= 0xffffffffull) { fprintf(stderr, "[wfagpu] snapshot arena exceeds 32-bit offsets\n"); return -1; }
     }
@@ -632,6 +644,23 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.n_items = (uint32_t)n_items;
     kp.queue = s.counters.p + CTR_QUEUE;
     kp.tb_queue = s.counters.p + CTR_TBQ;
+    kp.bound_queue = s.counters.p + CTR_BQ;
+    /* per-pair bounds: first pass of the packed exact path only (a re-dispatched pair never
+     * depends on them) */
+    bool use_bound = !banded && !ascii && first_pass && !d->no_bound;
+    if (use_bound && !d->force_bound) {
+        /* Worth it?  With D = d_end - 1 and a typical score m, the launch bound leaves
+         * cells(D/m) * m^2 cells per pair (cells(r) = r^2/4 + (1.5r - 1)(1 - r/2), 1 from r = 2 on), the
+         * pair's own bound 0.5 * m^2; the bound pass costs ~32 cells per score at ~3x the cost per
+         * cell (measured on B200: ~240 against ~2.75 warp instructions). */
+        const bool hinted = d_want < d_full && d->hint_mean > 0;
+        const double m = hinted ? d->hint_mean : 0.5 * (d_end - 1);
+        const double r = std::min(2.0, std::max(1.0, (d_end - 1) / std::max(1.0, m)));
+        const double cells = r * r / 4 + (1.5 * r - 1) * (1 - r / 2);
+        use_bound = (cells - 0.5) * m > 130.0;
+    }
+    if (use_bound && s.bound.ensure(s.n + 1)) return -1;
+    kp.bound = use_bound ? s.bound.p : nullptr;
     kp.steps = s.steps.p;
     kp.d_end = d_end;
     kp.n_cap = c.n_cap;
@@ -674,10 +703,26 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         if (occ < 1) { fprintf(stderr, "[wfagpu] traceback kernel does not fit\n"); return -1; }
         tb_ctas = occ * d->prop.multiProcessorCount;
     }
+    int bound_ctas = 0;
+    constexpr int kBoundWarps = 8;
+    if (use_bound) {
+        const int occ = bound_max_ctas_per_sm(c.A, c.E1, kBoundWarps);
+        if (occ < 1) kp.bound = nullptr; else bound_ctas = occ * d->prop.multiProcessorCount;
+    }
     for (size_t off = 0; off < n_items; off += items_per_launch) {
         const size_t cnt = std::min(items_per_launch, n_items - off);
         kp.order = order_dev + off;
         kp.n_items = (uint32_t)cnt;
+        if (kp.bound) {
+            CK(cudaMemsetAsync(s.counters.p + CTR_BQ, 0, sizeof(uint32_t), s.stream));
+            const int ctas = (int)std::min<size_t>((size_t)bound_ctas, (cnt + kBoundWarps - 1) / kBoundWarps);
+            cudaError_t eb = launch_bound(kp, ctas, kBoundWarps, s.stream);
+            if (eb != cudaSuccess) {
+                fprintf(stderr, "[wfagpu] bound kernel launch failed: %s\n", cudaGetErrorString(eb));
+                return -1;
+            }
+            s.stats.launches += 1;
+        }
         CK(cudaMemsetAsync(s.counters.p + CTR_QUEUE, 0, sizeof(uint32_t), s.stream));
         cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
                                : launch_exact(kp, c.group_threads, c.groups_per_cta, (int)std::min<size_t>(c.ctas, cnt), c.smem, ascii, s.stream);

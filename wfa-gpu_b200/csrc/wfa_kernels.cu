@@ -267,6 +267,26 @@ __device__ __forceinline__ int extend_ascii(const char *__restrict__ P, const ch
     return off + acc;
 }
 
+/* extend_packed on the packed words in global memory (the warp-per-pair kernels) */
+__device__ __forceinline__ int extend_packed_g(const uint32_t *__restrict__ Pw, const uint32_t *__restrict__ Tw,
+                                               int plen, int tlen, int k, int off)
+{
+    const int v = off - k, h = off;
+    const int rem = min(plen - v, tlen - h);
+    if (rem < 0) return kOffNull;
+    int acc = 0;
+    while (acc < rem) {
+        const uint32_t v2 = (uint32_t)(v + acc), h2 = (uint32_t)(h + acc);
+        const uint32_t a = __ldg(Pw + (v2 >> 3)) << ((v2 & 7u) * 2u);
+        const uint32_t b = __ldg(Tw + (h2 >> 3)) << ((h2 & 7u) * 2u);
+        const int nv = 16 - (int)max(v2 & 7u, h2 & 7u);
+        const int eq = min(__clz((int)(a ^ b)) >> 1, nv);
+        acc += eq;
+        if (eq < nv) break;
+    }
+    return off + min(acc, rem);
+}
+
 /* Score-bound pruning window of one score: the diagonals of [-n, n] within q = (Dmax - d) / e of
  * the target diagonal.  When none is (an all-NULL step) the window is the clamped full range, so
  * that the rows still read as NULL wherever a later score may look.  Returns whether any cell is
@@ -460,13 +480,14 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                     }
                 };
                 /* Score-bound pruning: this launch only reports pairs that finish with a score
-                 * <= Dmax = d_end - 1, and every diagonal between k and the target diagonal kt costs
+                 * <= Dmax (d_end - 1, or the pair's own bound from wfa_bound_kernel), and every diagonal between k and the target diagonal kt costs
                  * at least one gap extension, so a cell (d, k) with d + e * |k - kt| > Dmax cannot be
                  * on such an alignment.  Those cells are not computed and read as NULL; the cells of
                  * the optimal path keep their offsets and win the same tie-breaks (proof and
                  * poisoned-cell model: oracle/kernel_model.c, km_prune_range).  (Dmax - d) = q*e + r. */
-                int pr_q = (p.d_end - 1) / e, pr_r = (p.d_end - 1) % e;
-                for (int d = 1; d < p.d_end; ++d) {
+                const int Dmax = p.bound ? min(p.d_end - 1, p.bound[idx]) : p.d_end - 1;
+                int pr_q = Dmax / e, pr_r = Dmax % e;
+                for (int d = 1; d <= Dmax; ++d) {
                     const wfagpu_step_t st = st_next;
                     if (d + 1 < p.d_end) st_next = p.steps[d + 1];
                     const int n = st.n;
@@ -639,6 +660,122 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
 }
 
 /* ======================================================================== */
+/*              score upper bound (warp per pair, 32 diagonals)             */
+/* ======================================================================== */
+/*
+ * Feeds the score-bound pruning of wfa_exact_kernel with a per-pair bound.  A warp runs the
+ * same M/I/D recurrence on a window of 32 diagonals (one per lane) that is re-centred every
+ * few scores on the diagonal closest to the end of both sequences -- the idea of the
+ * reference's adaptive band (sequence_distance_kernel_aband.cu:99-147) at the width of a warp.
+ * Every offset it holds is the end of a real partial alignment, so the score at which it
+ * reaches (plen, tlen) is the score of a real alignment: an upper bound of the optimum, and
+ * in practice the optimum itself (16 diagonals already find it on 10 kbp / 5 % reads).
+ * Its result only narrows the exact kernel's work, never its result: any bound >= the optimum
+ * gives identical scores and CIGARs, and a pair that misses here just keeps the launch bound.
+ * Cost: 32 cells per score against ~score/2 in the exact kernel.
+ */
+constexpr int kBoundNull = -(1 << 28);
+
+__global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ KernelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = p.x, e = p.e, A = p.A, E1 = p.E1, oe = p.o + p.e;
+    const int rows = A + 2 * E1;
+    /* per warp: rows x 32 offsets.  Every row shares one window [wlo, wlo + 31]; diagonal k lives in
+     * slot k & 31, so moving the window only has to clear the slots that change owner. */
+    int *const ring = reinterpret_cast<int *>(smem_raw) + (size_t)warp * (rows * 32);
+    int *const Mr = ring, *const Ir = ring + A * 32, *const Dr = Ir + E1 * 32;
+    const int Dlaunch = p.d_end - 1;
+    const int slotL = (lane + 31) & 31, slotR = (lane + 1) & 31;
+
+    while (true) {
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(p.bound_queue, 1u);
+        pos = __shfl_sync(FULL, pos, 0);
+        if (pos >= p.n_items) break;
+        const uint32_t idx = p.order[pos];
+        const wfagpu_pair_t pr = p.pairs[idx];
+        if (pr.flags & WFAGPU_PAIR_HAS_N) { if (lane == 0) p.bound[idx] = Dlaunch; continue; }
+        const int plen = (int)pr.plen, tlen = (int)pr.tlen, kt = tlen - plen;
+        const uint32_t *const Pw = p.packed + pr.p_word;
+        const uint32_t *const Tw = p.packed + pr.t_word;
+        for (int r = 0; r < rows; ++r) ring[r * 32 + lane] = kBoundNull;
+        int wlo = -16;
+        int result = Dlaunch;
+        {
+            const int m = extend_packed_g(Pw, Tw, plen, tlen, 0, 0);
+            if (lane == 0) Mr[0] = m;                       /* score 0: k = 0 sits in slot 0 */
+            if (kt == 0 && m == tlen) result = 0;
+        }
+        __syncwarp();
+        if (result != 0) {
+            /* ring rows of the current score and of its sources, stepped with the score */
+            int mc = 0, mx = (A - x) % A, mo = (A - oe) % A, ic = 0, ie = (E1 - e) % E1;
+            int my_m = kBoundNull, my_k = 0;
+            wfagpu_step_t st_next = p.steps[1 < p.d_end ? 1 : 0];
+            for (int d = 1; d <= Dlaunch; ++d) {
+                const wfagpu_step_t st = st_next;
+                if (d + 1 < p.d_end) st_next = p.steps[d + 1];
+                if (++mc == A) mc = 0;
+                if (++mx == A) mx = 0;
+                if (++mo == A) mo = 0;
+                if (++ic == E1) ic = 0;
+                if (++ie == E1) ie = 0;
+                if ((d & 7) == 0) {
+                    /* re-centre on the diagonal with the least sequence left */
+                    unsigned key = 0xffffffffu;
+                    if (my_m >= 0) key = ((unsigned)max((plen - (my_m - my_k)) + (tlen - my_m), 0) << 5) | (unsigned)lane;
+                    const unsigned best = __reduce_min_sync(FULL, key);
+                    if (best != 0xffffffffu) {
+                        const int nlo = __shfl_sync(FULL, my_k, (int)(best & 31u)) - 16;
+                        if (nlo != wlo) {
+                            const int k_old = wlo + ((lane - wlo) & 31), k_new = nlo + ((lane - nlo) & 31);
+                            if (k_old != k_new)
+                                for (int r = 0; r < rows; ++r) ring[r * 32 + lane] = kBoundNull;
+                            wlo = nlo;
+                            __syncwarp();
+                        }
+                    }
+                }
+                const int k = wlo + ((lane - wlo) & 31);
+                int vM = kBoundNull, vI = kBoundNull, vD = kBoundNull;
+                if (st.kind != WFAGPU_STEP_NULL) {
+                    const int n = st.n;
+                    if (k >= -n && k <= n) {
+                        vM = Mr[mx * 32 + lane] + 1;
+                        if (st.kind == WFAGPU_STEP_MDI) {
+                            const bool okL = (k != wlo), okR = (k != wlo + 31);
+                            const int moL = okL ? Mr[mo * 32 + slotL] : kBoundNull;
+                            const int ieL = okL ? Ir[ie * 32 + slotL] : kBoundNull;
+                            const int moR = okR ? Mr[mo * 32 + slotR] : kBoundNull;
+                            const int deR = okR ? Dr[ie * 32 + slotR] : kBoundNull;
+                            vI = max(moL, ieL) + 1;
+                            vD = max(moR, deR);
+                            vM = max(max(vM, vD), vI);
+                        }
+                        if (vM >= 0) vM = extend_packed_g(Pw, Tw, plen, tlen, k, vM);
+                        if (vM < 0) vM = kBoundNull;
+                        if (vI < 0) vI = kBoundNull;
+                        if (vD < 0) vD = kBoundNull;
+                    }
+                    my_m = vM; my_k = k;
+                }
+                /* the rows being replaced (scores d - A, d - e - 1) are no source of this score */
+                Mr[mc * 32 + lane] = vM;
+                Ir[ic * 32 + lane] = vI;
+                Dr[ic * 32 + lane] = vD;
+                __syncwarp();
+                if (__any_sync(FULL, k == kt && vM == tlen)) { result = d; break; }
+            }
+        }
+        if (lane == 0) p.bound[idx] = result;
+        __syncwarp();
+    }
+}
+
+/* ======================================================================== */
 /*                 checkpointed traceback (warp per pair)                   */
 /* ======================================================================== */
 /*
@@ -653,25 +790,6 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
  * Running it as its own kernel puts thousands of these latency-bound walks in flight
  * instead of one per resident CTA (model: oracle/kernel_model.c, km_align_pair_ckpt).
  */
-__device__ __forceinline__ int extend_packed_g(const uint32_t *__restrict__ Pw, const uint32_t *__restrict__ Tw,
-                                               int plen, int tlen, int k, int off)
-{
-    const int v = off - k, h = off;
-    const int rem = min(plen - v, tlen - h);
-    if (rem < 0) return kOffNull;
-    int acc = 0;
-    while (acc < rem) {
-        const uint32_t v2 = (uint32_t)(v + acc), h2 = (uint32_t)(h + acc);
-        const uint32_t a = __ldg(Pw + (v2 >> 3)) << ((v2 & 7u) * 2u);
-        const uint32_t b = __ldg(Tw + (h2 >> 3)) << ((h2 & 7u) * 2u);
-        const int nv = 16 - (int)max(v2 & 7u, h2 & 7u);
-        const int eq = min(__clz((int)(a ^ b)) >> 1, nv);
-        acc += eq;
-        if (eq < nv) break;
-    }
-    return off + min(acc, rem);
-}
-
 template <bool ASCII, int P>
 __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constant__ KernelParams p)
 {
@@ -718,7 +836,8 @@ __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constan
         uint32_t *const ops = p.ops_pool + ops_off;
 
         const int m00 = extend(0, 0);
-        const int kt = tlen - plen, Dmax = p.d_end - 1;        /* same pruning window as the forward pass */
+        const int kt = tlen - plen;                              /* same pruning window as the forward pass */
+        const int Dmax = p.bound ? min(p.d_end - 1, p.bound[idx]) : p.d_end - 1;
         int cd = dist, ck = kt, comp = 0;
         uint32_t word = 0, n_ops = 0;
         while (!(comp == 0 && cd == 0) && tb_ok) {
@@ -1379,6 +1498,26 @@ size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups
     return group_bytes * (size_t)groups_per_cta;
 }
 
+size_t bound_smem_bytes(int A, int E1, int warps) { return (size_t)warps * (size_t)(A + 2 * E1) * 32 * sizeof(int); }
+
+cudaError_t launch_bound(const KernelParams &p, int ctas, int warps, cudaStream_t s)
+{
+    const size_t smem = bound_smem_bytes(p.A, p.E1, warps);
+    cudaError_t err = cudaFuncSetAttribute(wfa_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    wfa_bound_kernel<<<ctas, 32 * warps, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+int bound_max_ctas_per_sm(int A, int E1, int warps)
+{
+    const size_t smem = bound_smem_bytes(A, E1, warps);
+    int n = 0;
+    if (cudaFuncSetAttribute(wfa_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfa_bound_kernel, 32 * warps, smem) != cudaSuccess) return 0;
+    return n;
+}
+
 size_t traceback_smem_bytes(int A, int period, int warps)
 {
     const size_t per_warp = ((size_t)3 * (period + A - 1) * (2 * period + 1) * 2 + 15) & ~(size_t)15;
@@ -1389,9 +1528,10 @@ using tb_kernel_t = void (*)(const KernelParams);
 static tb_kernel_t traceback_fn(bool ascii, int period)
 {
     switch (period) {
-    case 8: return ascii ? wfa_traceback_kernel<true, 8> : wfa_traceback_kernel<false, 8>;
-    case 16: return ascii ? wfa_traceback_kernel<true, 16> : wfa_traceback_kernel<false, 16>;
-    case 32: return ascii ? wfa_traceback_kernel<true, 32> : wfa_traceback_kernel<false, 32>;
+    /* 2P + 1 diagonals at the base of a cone: 15 and 31 keep a level within one and two warp passes */
+    case 7: return ascii ? wfa_traceback_kernel<true, 7> : wfa_traceback_kernel<false, 7>;
+    case 15: return ascii ? wfa_traceback_kernel<true, 15> : wfa_traceback_kernel<false, 15>;
+    case 31: return ascii ? wfa_traceback_kernel<true, 31> : wfa_traceback_kernel<false, 31>;
     default: return nullptr;
     }
 }

@@ -38,6 +38,9 @@ struct KernelParams {
     uint32_t n_items;             /* entries of `order`                                      */
     uint32_t *queue;              /* atomic work-queue head                                  */
     uint32_t *tb_queue;           /* same for the traceback kernel                           */
+    uint32_t *bound_queue;        /* same for the bound kernel                               */
+    int32_t *bound;               /* per pair: upper bound of its score (wfa_bound_kernel), or null:
+                                   * the pruning then uses the launch bound d_end - 1         */
     const wfagpu_step_t *steps;
     int d_end;                    /* scores 1 .. d_end-1 may be computed                     */
     int n_cap;                    /* largest half width the rings of this launch can hold    */
@@ -59,7 +62,7 @@ struct KernelParams {
     uint64_t arena_units;         /* uint4 units per group                                   */
     const uint32_t *ck_off;       /* checkpointed traceback: arena offset (units) of the snapshot of
                                    * score j * ck_period; null = one decision byte per cell  */
-    int ck_period;                /* 8, 16 or 32                                              */
+    int ck_period;                /* 7, 15 or 31                                              */
     uint32_t *ops_scratch;        /* per-group scratch for the traceback's op words          */
     uint32_t ops_scratch_words;
     /* outputs */
@@ -101,6 +104,10 @@ void launch_cigar_text(const CigarParams &p, cudaStream_t s);
 /* group_threads == 32 -> warp-per-pair variant; otherwise CTA-per-pair */
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
                          size_t smem_bytes, bool ascii_extend, cudaStream_t s);
+/* per-pair score upper bounds for the pruning (warp per pair) */
+cudaError_t launch_bound(const KernelParams &p, int ctas, int warps, cudaStream_t s);
+size_t bound_smem_bytes(int A, int E1, int warps);
+int bound_max_ctas_per_sm(int A, int E1, int warps);
 /* traceback of the checkpointed path: `warps` pairs per CTA */
 cudaError_t launch_traceback(const KernelParams &p, int ctas, int warps, bool ascii_extend, cudaStream_t s);
 size_t traceback_smem_bytes(int A, int period, int warps);
