@@ -98,6 +98,8 @@ typedef struct {
     uint32_t ascii_pairs;     /* pairs routed to the byte-compare kernel        */
     uint64_t cells;           /* wavefront cells computed (0 unless profiling)  */
     uint64_t h2d_bytes, d2h_bytes;
+    float ms_wavefront;       /* the first pass's wavefront kernel alone (0 if it ran in several sub-launches) */
+    float reserved0;
 } wfagpu_batch_stats_t;
 
 /* Opens (or returns the cached) context of CUDA device `dev`. NULL on failure

@@ -97,7 +97,8 @@ struct LaunchCfg {
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool wf_timed = false;             /* ev[6], ev[7] bracket the first pass's wavefront kernel */
     DevBuf<char> ascii;
     DevBuf<uint32_t> packed;
     DevBuf<wfagpu_pair_t> pairs;
@@ -339,7 +340,7 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
     bool large = d->force_large || max_len >= (1u << 15);
     if (!large) {
         /* rings that do not fit one CTA's shared memory even single-buffered go to the large tier */
-        if (exact_smem_bytes(A, E1, rs(n_want), seq_words, 1, 1) > smem_max) large = true;
+        if (exact_smem_bytes(A, E1, rs(n_want), seq_words, 1, 1, true) > smem_max) large = true;
     }
     if (large) {
         c->global_ring = true;
@@ -389,18 +390,18 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
             const size_t budget = std::min(smem_max, smem_sm / k - 1024);
             for (int st = 2; st >= 1; --st) {
                 if (d->force_stages && st != d->force_stages) continue;
-                const size_t need = exact_smem_bytes(A, E1, rs(n_want), seq_words, 1, st);
+                const size_t need = exact_smem_bytes(A, E1, rs(n_want), seq_words, 1, st, true);
                 if (need <= budget) { best_k = k; stages = st; smem = need; break; }
             }
         }
         if (!best_k) {
             /* does not fit even alone: hold as many diagonals as one CTA can */
             stages = 1;
-            const size_t fixed = exact_smem_bytes(A, E1, 0, seq_words, 1, stages);
+            const size_t fixed = exact_smem_bytes(A, E1, 0, seq_words, 1, stages, true);
             if (fixed + (size_t)rows * rs(1) * 2 > smem_max) return -2;   /* the sequences alone do not fit */
             n_cap = (int)((smem_max - fixed - 64) / ((size_t)rows * 4)) - 2 * G - (ck ? 16 : 2);
             if (n_cap < 1) return -2;
-            smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages);
+            smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages, true);
             best_k = 1;
         }
         c->stages = stages;
@@ -724,12 +725,15 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
             s.stats.launches += 1;
         }
         CK(cudaMemsetAsync(s.counters.p + CTR_QUEUE, 0, sizeof(uint32_t), s.stream));
+        const bool time_it = first_pass && items_per_launch >= n_items && s.ev[6] && s.ev[7];
+        if (time_it) CK(cudaEventRecord(s.ev[6], s.stream));
         cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
                                : launch_exact(kp, c.group_threads, c.groups_per_cta, (int)std::min<size_t>(c.ctas, cnt), c.smem, ascii, s.stream);
         if (e != cudaSuccess) {
             fprintf(stderr, "[wfagpu] alignment kernel launch failed: %s\n", cudaGetErrorString(e));
             return -1;
         }
+        if (time_it) { CK(cudaEventRecord(s.ev[7], s.stream)); s.wf_timed = true; }
         s.stats.launches += 1;
         if (c.ckpt) {
             /* ring snapshots -> 2-bit ops, a warp per pair */
@@ -803,11 +807,12 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
     s.stats.launches += 1;
     CK(cudaEventRecord(s.ev[3], s.stream));
     s.last_d_end = 0;
+    s.wf_timed = false;
     int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, true, true, &s.capped);
     if (rc) return rc;
-    CK(cudaEventRecord(s.ev[4], s.stream));
     d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;   /* re-read: tests flip it between runs */
     if (plan->with_cigar && d->device_text && enqueue_text(d, s, n, s.last_d_end)) return -1;
+    CK(cudaEventRecord(s.ev[4], s.stream));                  /* align time = bound + wavefronts + traceback + CIGAR text */
     return 0;
 }
 
@@ -911,6 +916,8 @@ extern "C" int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, 
     CK(cudaStreamSynchronize(s.stream));
     if (ms_pack) cudaEventElapsedTime(ms_pack, s.ev[2], s.ev[3]);
     if (ms_align) cudaEventElapsedTime(ms_align, s.ev[3], s.ev[4]);
+    s.stats.ms_wavefront = 0;
+    if (s.wf_timed) cudaEventElapsedTime(&s.stats.ms_wavefront, s.ev[6], s.ev[7]);
     if (s.n && d->use_hint) {
         /* read the result records back (16 B per pair) so that a re-run of the resident
          * batch is provisioned like the next batch of a stream would be */

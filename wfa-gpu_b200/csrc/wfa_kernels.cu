@@ -178,6 +178,10 @@ __device__ __forceinline__ void sts_16(uint32_t a, int v)
 {
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory");
 }
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 {
     uint4 v;
@@ -309,6 +313,22 @@ struct GroupCtl {
     uint32_t pad[2];
 };
 
+/* Per-score schedule record (CTA-per-pair kernels with shared-memory rings).  Everything a thread
+ * needs to start a score -- the pruning window, the step kind, the ring rows of the score and of
+ * its sources -- is the same for the whole CTA and costs ~60 instructions to derive, a third of
+ * what a warp spends on a score at 10 kbp / 5 %.  Warp 0 derives the records of 32 scores at a
+ * time (one per lane, double-buffered in shared memory) and every thread fetches its score's
+ * record with three 128-bit broadcast loads. */
+struct __align__(16) StepRec {
+    int lo, hi;             /* window of diagonals computed at this score                       */
+    uint32_t flags;         /* bits 1:0 kind, 2 live, 3 stop, 4 target diagonal inside, 5 snapshot */
+    int n;                  /* half width of the unpruned wavefront (snapshot pitch)            */
+    uint32_t aMc, aMx, aMo, aIc;
+    uint32_t aIe, aDc, aDe, ck_j;   /* ck_j: snapshot index (CKPT) or decision-byte row offset */
+};
+constexpr uint32_t kRecLive = 4u, kRecStop = 8u, kRecTarget = 16u, kRecSnap = 32u;
+constexpr uint32_t kSchedBytes = 2u * 32u * (uint32_t)sizeof(StepRec);
+
 /* CKPT (CTA per pair, shared-memory rings, with backtrace): instead of a decision byte per
  * cell the forward pass snapshots the ring rows every p.ck_period scores, and the traceback
  * recomputes the offsets it needs on the dependency cone below the cell it stands on
@@ -320,6 +340,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
     using G = Group<WARP>;
     using RA = typename R::addr_t;
     constexpr bool GR = (R::kElem == 4);          /* rings in global memory */
+    constexpr bool SCHED = !WARP && !GR;          /* per-score schedule records (see StepRec) */
     constexpr int NULLV = R::kNull;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -334,11 +355,12 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
     const uint32_t ring_bytes = GR ? 0u : (((uint32_t)rows * row_bytes + 15u) & ~15u);
     const uint32_t seq_bytes = (uint32_t)p.seq_words * 4u;          /* one sequence, one stage */
     const uint32_t seq_total = ASCII ? 0u : 2u * (uint32_t)p.stages * seq_bytes;
-    const uint32_t group_bytes = (ring_bytes + seq_total + (uint32_t)sizeof(GroupCtl) + 15u) & ~15u;
+    const uint32_t group_bytes = (ring_bytes + seq_total + (uint32_t)sizeof(GroupCtl) + (SCHED ? kSchedBytes : 0u) + 15u) & ~15u;
     unsigned char *gbase = smem_raw + (size_t)G::id_in_cta() * group_bytes;
     const uint32_t ring_sa = smem_u32(gbase);
     const uint32_t seq_sa = ring_sa + ring_bytes;
     GroupCtl *ctl = reinterpret_cast<GroupCtl *>(gbase + ring_bytes + seq_total);
+    const uint32_t sched_sa = ring_sa + ring_bytes + seq_total + (uint32_t)sizeof(GroupCtl);   /* GroupCtl is 48 bytes */
 
     const int x = p.x, e = p.e, A = p.A, E1 = p.E1, GW = p.G;
     const int oe = p.o + p.e;
@@ -432,7 +454,51 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
         bool finished = false;
 
         if (!skip) {
+            /* Score-bound pruning: this launch only reports pairs that finish with a score <= Dmax
+             * (d_end - 1, or the pair's own bound from wfa_bound_kernel), and every diagonal between k
+             * and the target diagonal kt costs at least one gap extension, so a cell (d, k) with
+             * d + e * |k - kt| > Dmax cannot be on such an alignment.  Those cells are not computed and
+             * read as NULL; the cells of the optimal path keep their offsets and win the same
+             * tie-breaks (proof and poisoned-cell model: oracle/kernel_model.c, km_prune_range). */
+            const int Dmax = p.bound ? min(p.d_end - 1, p.bound[idx]) : p.d_end - 1;
+            /* schedule records of scores dbase .. dbase + 31 (warp 0, one score per lane) */
+            auto fill_sched = [&](int dbase, int buf) {
+                if constexpr (SCHED) {
+                    const int d = dbase + tid;
+                    StepRec r;
+                    r.lo = 0; r.hi = -1; r.flags = kRecStop; r.n = 0; r.ck_j = 0;
+                    r.aMc = r.aMx = r.aMo = r.aIc = r.aIe = r.aDc = r.aDe = 0;
+                    if (d <= Dmax) {
+                        const wfagpu_step_t st = p.steps[d];
+                        int lo, hi;
+                        const bool live = prune_window((int)st.n, kt, (Dmax - d) / e, p.n_cap, lo, hi);
+                        const bool stop = live && (lo < -p.n_cap || hi > p.n_cap);     /* wider than the rings */
+                        const bool work = live && st.kind != WFAGPU_STEP_NULL;
+                        r.lo = lo; r.hi = hi; r.n = (int)st.n;
+                        r.flags = (uint32_t)st.kind | (live ? kRecLive : 0u) | (stop ? kRecStop : 0u) |
+                                  ((work && kt >= lo && kt <= hi) ? kRecTarget : 0u) |
+                                  ((CKPT && d % p.ck_period == 0) ? kRecSnap : 0u);
+                        r.ck_j = CKPT ? (uint32_t)(d / p.ck_period) : st.row_off;    /* snapshot index, or decision row */
+                        const int dm = d % A, de1 = d % E1;
+                        int sx = dm - x % A; if (sx < 0) sx += A;
+                        int so = dm - oe % A; if (so < 0) so += A;
+                        int se = de1 - e % E1; if (se < 0) se += E1;
+                        r.aMc = (uint32_t)M0 + (uint32_t)dm * row_bytes;
+                        r.aMx = (uint32_t)M0 + (uint32_t)sx * row_bytes;
+                        r.aMo = (uint32_t)M0 + (uint32_t)so * row_bytes;
+                        r.aIc = (uint32_t)I0 + (uint32_t)de1 * row_bytes;
+                        r.aIe = (uint32_t)I0 + (uint32_t)se * row_bytes;
+                        r.aDc = (uint32_t)D0 + (uint32_t)de1 * row_bytes;
+                        r.aDe = (uint32_t)D0 + (uint32_t)se * row_bytes;
+                    }
+                    const uint32_t a = sched_sa + (uint32_t)(buf * 32 + tid) * (uint32_t)sizeof(StepRec);
+                    sts_v4(a, make_uint4((uint32_t)r.lo, (uint32_t)r.hi, r.flags, (uint32_t)r.n));
+                    sts_v4(a + 16u, make_uint4(r.aMc, r.aMx, r.aMo, r.aIc));
+                    sts_v4(a + 32u, make_uint4(r.aIe, r.aDc, r.aDe, r.ck_j));
+                }
+            };
             if (tid == 0) R::st(M0, 0, extend(0, 0));
+            if (SCHED && tid < 32) fill_sched(1, 0);
             G::sync();
             if (kt == 0 && R::ld(M0, 0) == tlen) {
                 finished = true;
@@ -479,41 +545,60 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                         }
                     }
                 };
-                /* Score-bound pruning: this launch only reports pairs that finish with a score
-                 * <= Dmax (d_end - 1, or the pair's own bound from wfa_bound_kernel), and every diagonal between k and the target diagonal kt costs
-                 * at least one gap extension, so a cell (d, k) with d + e * |k - kt| > Dmax cannot be
-                 * on such an alignment.  Those cells are not computed and read as NULL; the cells of
-                 * the optimal path keep their offsets and win the same tie-breaks (proof and
-                 * poisoned-cell model: oracle/kernel_model.c, km_prune_range).  (Dmax - d) = q*e + r. */
-                const int Dmax = p.bound ? min(p.d_end - 1, p.bound[idx]) : p.d_end - 1;
-                int pr_q = Dmax / e, pr_r = Dmax % e;
+                int pr_q = Dmax / e, pr_r = Dmax % e;        /* (Dmax - d) = q * e + r */
+                unsigned long long n_cells = 0;              /* cells computed for this pair (optional counter) */
                 for (int d = 1; d <= Dmax; ++d) {
-                    const wfagpu_step_t st = st_next;
-                    if (d + 1 < p.d_end) st_next = p.steps[d + 1];
-                    const int n = st.n;
-                    if (pr_r == 0) { pr_r = e - 1; --pr_q; } else --pr_r;
-                    int lo, hi;
-                    const bool live = prune_window(n, kt, pr_q, p.n_cap, lo, hi);
-                    if (live && (lo < -p.n_cap || hi > p.n_cap)) break;     /* wider than the rings of this launch */
-                    aMc = R::add(aMc, row_bytes); if (aMc == Mend) aMc = M0;
-                    aMx = R::add(aMx, row_bytes); if (aMx == Mend) aMx = M0;
-                    aMo = R::add(aMo, row_bytes); if (aMo == Mend) aMo = M0;
-                    aIc = R::add(aIc, row_bytes); if (aIc == Iend) aIc = I0;
-                    aIe = R::add(aIe, row_bytes); if (aIe == Iend) aIe = I0;
-                    aDc = R::add(aDc, row_bytes); if (aDc == Dend) aDc = D0;
-                    aDe = R::add(aDe, row_bytes); if (aDe == Dend) aDe = D0;
+                    int n, lo, hi, kind;
+                    uint32_t row_off = 0;                        /* decision-byte row of this score (!CKPT) */
+                    bool live, target_in, snap_now;
+                    if constexpr (SCHED) {
+                        const int ri = (d - 1) & 31, buf = ((d - 1) >> 5) & 1;
+                        if (ri == 0 && tid < 32) fill_sched(d + 32, buf ^ 1);       /* the block after this one */
+                        const uint32_t a = sched_sa + (uint32_t)(buf * 32 + ri) * (uint32_t)sizeof(StepRec);
+                        const uint4 r0 = lds_v4(a), r1 = lds_v4(a + 16u), r2 = lds_v4(a + 32u);
+                        if (r0.z & kRecStop) break;
+                        lo = (int)r0.x; hi = (int)r0.y; n = (int)r0.w;
+                        kind = (int)(r0.z & 3u);
+                        live = (r0.z & kRecLive) != 0;
+                        target_in = (r0.z & kRecTarget) != 0;
+                        snap_now = (r0.z & kRecSnap) != 0;
+                        aMc = r1.x; aMx = r1.y; aMo = r1.z; aIc = r1.w;
+                        aIe = r2.x; aDc = r2.y; aDe = r2.z;
+                        if (CKPT) ck_j = (int)r2.w; else row_off = r2.w;
+                        if (p.cells && live && kind != WFAGPU_STEP_NULL) n_cells += (unsigned)(hi - lo + 1);
+                    } else {
+                        const wfagpu_step_t st = st_next;
+                        if (d + 1 < p.d_end) st_next = p.steps[d + 1];
+                        n = st.n;
+                        kind = st.kind;
+                        row_off = st.row_off;
+                        if (pr_r == 0) { pr_r = e - 1; --pr_q; } else --pr_r;
+                        live = prune_window(n, kt, pr_q, p.n_cap, lo, hi);
+                        if (live && (lo < -p.n_cap || hi > p.n_cap)) break;     /* wider than the rings of this launch */
+                        if (live && kind != WFAGPU_STEP_NULL) n_cells += (unsigned)(hi - lo + 1);
+                        target_in = live && kind != WFAGPU_STEP_NULL && kt >= lo && kt <= hi;
+                        aMc = R::add(aMc, row_bytes); if (aMc == Mend) aMc = M0;
+                        aMx = R::add(aMx, row_bytes); if (aMx == Mend) aMx = M0;
+                        aMo = R::add(aMo, row_bytes); if (aMo == Mend) aMo = M0;
+                        aIc = R::add(aIc, row_bytes); if (aIc == Iend) aIc = I0;
+                        aIe = R::add(aIe, row_bytes); if (aIe == Iend) aIe = I0;
+                        aDc = R::add(aDc, row_bytes); if (aDc == Dend) aDc = D0;
+                        aDe = R::add(aDe, row_bytes); if (aDe == Dend) aDe = D0;
+                        snap_now = false;
+                        if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; snap_now = true; }
+                    }
 
-                    if (st.kind == WFAGPU_STEP_NULL || !live) {
+                    if (kind == WFAGPU_STEP_NULL || !live) {
                         for (int k = lo - GW + tid; k <= hi + GW; k += gsz) {
                             R::st(aMc, k, NULLV);
                             R::st(aIc, k, NULLV);
                             R::st(aDc, k, NULLV);
                         }
                         G::sync();
-                        if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n, lo, hi); }
+                        if (CKPT && snap_now) checkpoint(n, lo, hi);
                         continue;
                     }
-                    if (st.kind == WFAGPU_STEP_M) {
+                    if (kind == WFAGPU_STEP_M) {
                         for (int k = lo - GW + tid; k <= hi + GW; k += gsz) {
                             R::st(aIc, k, NULLV);
                             R::st(aDc, k, NULLV);
@@ -534,7 +619,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                         }
                         /* one decision byte per cell: bit0 I extends, bit1 D extends, bits 3:2 the winner of M
                          * (1 = I, 2 = X, 3 = D); a warp writes 32 consecutive bytes of the pair's row */
-                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + st.row_off) + n;
+                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + row_off) + n;
                         for (int k = lo + tid; k <= hi; k += gsz) {
                             const int io = R::ld(aMo, k - 1) + 1;
                             const int ie = R::ld(aIe, k - 1) + 1;
@@ -558,13 +643,14 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                         }
                     }
                     G::sync();
-                    if (kt >= lo && kt <= hi && R::ld(aMc, kt) == tlen) {
+                    if (target_in && R::ld(aMc, kt) == tlen) {
                         finished = true;
                         dist = d;
                         break;
                     }
-                    if (CKPT && --ck_left == 0) { ck_left = p.ck_period; ++ck_j; checkpoint(n, lo, hi); }
+                    if (CKPT && snap_now) checkpoint(n, lo, hi);
                 }
+                if (p.cells && tid == 0) atomicAdd(p.cells, n_cells);
             }
         }
 
@@ -1489,12 +1575,12 @@ static int occupancy_one(int threads, size_t smem)
     return n;
 }
 
-size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages)
+size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages, bool sched)
 {
     const int rows = A + 2 * E1;
     const size_t ring_bytes = ((size_t)rows * row_stride * sizeof(int16_t) + 15) & ~(size_t)15;
     const size_t seq_bytes = (size_t)seq_words * 4;
-    const size_t group_bytes = (ring_bytes + 2 * (size_t)stages * seq_bytes + sizeof(GroupCtl) + 15) & ~(size_t)15;
+    const size_t group_bytes = (ring_bytes + 2 * (size_t)stages * seq_bytes + sizeof(GroupCtl) + (sched ? kSchedBytes : 0) + 15) & ~(size_t)15;
     return group_bytes * (size_t)groups_per_cta;
 }
 

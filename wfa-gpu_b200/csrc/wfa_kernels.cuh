@@ -112,7 +112,8 @@ int bound_max_ctas_per_sm(int A, int E1, int warps);
 cudaError_t launch_traceback(const KernelParams &p, int ctas, int warps, bool ascii_extend, cudaStream_t s);
 size_t traceback_smem_bytes(int A, int period, int warps);
 int traceback_max_ctas_per_sm(int A, int period, int warps, bool ascii_extend);
-size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages);
+/* sched: CTA-per-pair kernels with shared-memory rings keep per-score schedule records (3 KB) */
+size_t exact_smem_bytes(int A, int E1, int row_stride, int seq_words, int groups_per_cta, int stages, bool sched = false);
 cudaError_t launch_banded(const KernelParams &p, int threads, int ctas, size_t smem_bytes, bool ascii_extend,
                           cudaStream_t s);
 size_t banded_smem_bytes(int A, int win, int seq_words, int stages);

@@ -69,7 +69,8 @@ class PairOut(C.Structure):
 class BatchStats(C.Structure):
     _fields_ = [("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("launches", C.c_uint32), ("redispatched", C.c_uint32),
-                ("ascii_pairs", C.c_uint32), ("cells", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("ascii_pairs", C.c_uint32), ("cells", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("ms_wavefront", C.c_float), ("reserved0", C.c_float)]
 
 
 class DevPair(C.Structure):
