@@ -319,7 +319,7 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
  * share an SM.  Measured on B200 (10 kbp / 5 %): 1 CTA x 1024 threads 62 k pairs/s,
  * 2 x 512 95 k, 3 x 384 109 k -- more, smaller CTAs hide the per-score barrier.
  * `n_want` is the half width the launch should be able to hold. */
-static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_t max_len, size_t n_items,
+static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_min, uint32_t max_len, size_t n_items,
                       bool ascii, bool bt, LaunchCfg *c)
 {
     const int A = std::max(o + e, x) + 1, E1 = e + 1, G = A;
@@ -385,13 +385,23 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, uint32_
         int best_k = 0, stages = 1, n_cap = n_want;
         size_t smem = 0;
         const int kmax = d->force_ctas_per_sm ? d->force_ctas_per_sm : 6;
+        /* n_min <= n_want: the rings may be provisioned below n_want (down to n_min) when that buys
+         * another resident CTA -- the few pairs that then outgrow them are re-dispatched */
+        n_min = std::max(1, std::min(n_min, n_want));
         for (int k = kmax; k >= 1 && !best_k; --k) {
             /* every resident CTA also reserves 1 KB of system shared memory */
             const size_t budget = std::min(smem_max, smem_sm / k - 1024);
             for (int st = 2; st >= 1; --st) {
                 if (d->force_stages && st != d->force_stages) continue;
-                const size_t need = exact_smem_bytes(A, E1, rs(n_want), seq_words, 1, st, true);
-                if (need <= budget) { best_k = k; stages = st; smem = need; break; }
+                if (exact_smem_bytes(A, E1, rs(n_min), seq_words, 1, st, true) > budget) continue;
+                int lo = n_min, hi = n_want;             /* widest rings that still fit k CTAs */
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) / 2;
+                    if (exact_smem_bytes(A, E1, rs(mid), seq_words, 1, st, true) <= budget) lo = mid; else hi = mid - 1;
+                }
+                best_k = k; stages = st; n_cap = lo;
+                smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, st, true);
+                break;
             }
         }
         if (!best_k) {
@@ -529,6 +539,10 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         return (int)best;
     };
     int n_want = plan.band > 0 ? n_full : n_need(d_want);
+    /* with a hint, rings for hint + 3 % are enough for (almost) every pair */
+    int n_min = n_want;
+    if (d_want < d_full && plan.band <= 0)
+        n_min = std::min(n_want, n_need((int)std::min<long long>((long long)d->hint_dist + d->hint_dist / 32 + 4, d_full - 1) + 1));
     const bool banded = plan.band > 0;
     LaunchCfg c{};
     int rc = 0;
@@ -559,7 +573,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         if (occ < 1) return -1;
         c.ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ * d->prop.multiProcessorCount, n_items));
     } else {
-        rc = choose_cfg(d, plan.x, plan.o, plan.e, n_want, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
+        rc = choose_cfg(d, plan.x, plan.o, plan.e, n_want, n_min, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
     }
     if (rc) return rc;
     /* scores this launch can reach and the decision units they need */

@@ -316,7 +316,7 @@ struct GroupCtl {
 /* Per-score schedule record (CTA-per-pair kernels with shared-memory rings).  Everything a thread
  * needs to start a score -- the pruning window, the step kind, the ring rows of the score and of
  * its sources -- is the same for the whole CTA and costs ~60 instructions to derive, a third of
- * what a warp spends on a score at 10 kbp / 5 %.  Warp 0 derives the records of 32 scores at a
+ * what a warp spends on a score at 10 kbp / 5 %.  Warp 0 derives the records of kSchedBlock scores at a
  * time (one per lane, double-buffered in shared memory) and every thread fetches its score's
  * record with three 128-bit broadcast loads. */
 struct __align__(16) StepRec {
@@ -327,7 +327,8 @@ struct __align__(16) StepRec {
     uint32_t aIe, aDc, aDe, ck_j;   /* ck_j: snapshot index (CKPT) or decision-byte row offset */
 };
 constexpr uint32_t kRecLive = 4u, kRecStop = 8u, kRecTarget = 16u, kRecSnap = 32u;
-constexpr uint32_t kSchedBytes = 2u * 32u * (uint32_t)sizeof(StepRec);
+constexpr int kSchedBlock = 16;                 /* scores per block of records (power of two, <= 32) */
+constexpr uint32_t kSchedBytes = 2u * kSchedBlock * (uint32_t)sizeof(StepRec);
 
 /* CKPT (CTA per pair, shared-memory rings, with backtrace): instead of a decision byte per
  * cell the forward pass snapshots the ring rows every p.ck_period scores, and the traceback
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
              * read as NULL; the cells of the optimal path keep their offsets and win the same
              * tie-breaks (proof and poisoned-cell model: oracle/kernel_model.c, km_prune_range). */
             const int Dmax = p.bound ? min(p.d_end - 1, p.bound[idx]) : p.d_end - 1;
-            /* schedule records of scores dbase .. dbase + 31 (warp 0, one score per lane) */
+            /* schedule records of scores dbase .. dbase + kSchedBlock - 1 (warp 0, one score per lane) */
             auto fill_sched = [&](int dbase, int buf) {
                 if constexpr (SCHED) {
                     const int d = dbase + tid;
@@ -491,14 +492,14 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                         r.aDc = (uint32_t)D0 + (uint32_t)de1 * row_bytes;
                         r.aDe = (uint32_t)D0 + (uint32_t)se * row_bytes;
                     }
-                    const uint32_t a = sched_sa + (uint32_t)(buf * 32 + tid) * (uint32_t)sizeof(StepRec);
+                    const uint32_t a = sched_sa + (uint32_t)(buf * kSchedBlock + tid) * (uint32_t)sizeof(StepRec);
                     sts_v4(a, make_uint4((uint32_t)r.lo, (uint32_t)r.hi, r.flags, (uint32_t)r.n));
                     sts_v4(a + 16u, make_uint4(r.aMc, r.aMx, r.aMo, r.aIc));
                     sts_v4(a + 32u, make_uint4(r.aIe, r.aDc, r.aDe, r.ck_j));
                 }
             };
             if (tid == 0) R::st(M0, 0, extend(0, 0));
-            if (SCHED && tid < 32) fill_sched(1, 0);
+            if (SCHED && tid < kSchedBlock) fill_sched(1, 0);
             G::sync();
             if (kt == 0 && R::ld(M0, 0) == tlen) {
                 finished = true;
@@ -552,9 +553,9 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
                     uint32_t row_off = 0;                        /* decision-byte row of this score (!CKPT) */
                     bool live, target_in, snap_now;
                     if constexpr (SCHED) {
-                        const int ri = (d - 1) & 31, buf = ((d - 1) >> 5) & 1;
-                        if (ri == 0 && tid < 32) fill_sched(d + 32, buf ^ 1);       /* the block after this one */
-                        const uint32_t a = sched_sa + (uint32_t)(buf * 32 + ri) * (uint32_t)sizeof(StepRec);
+                        const int ri = (d - 1) & (kSchedBlock - 1), buf = ((d - 1) / kSchedBlock) & 1;
+                        if (ri == 0 && tid < kSchedBlock) fill_sched(d + kSchedBlock, buf ^ 1);       /* the block after this one */
+                        const uint32_t a = sched_sa + (uint32_t)(buf * kSchedBlock + ri) * (uint32_t)sizeof(StepRec);
                         const uint4 r0 = lds_v4(a), r1 = lds_v4(a + 16u), r2 = lds_v4(a + 32u);
                         if (r0.z & kRecStop) break;
                         lo = (int)r0.x; hi = (int)r0.y; n = (int)r0.w;
