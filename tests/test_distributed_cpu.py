@@ -34,7 +34,9 @@ def test_gloo_world2_sharding_and_max_reduction(tmp_path):
         first = a.pair(0)[0]
         t_max, w_max = bench.reduce_max([1.0 + rank, 10.0 - rank])
         v = bench.aggregate_value(100, world, 3, t_max)
-        print(json.dumps(dict(rank=rank, world=world, first=first, t_max=t_max, w_max=w_max, v=v)))
+        # one file per rank: two ranks printing to the same pipe can interleave inside a line
+        with open(os.path.join({str(tmp_path)!r}, f"rank{{rank}}.json"), "w") as f:
+            json.dump(dict(rank=rank, world=world, first=first, t_max=t_max, w_max=w_max, v=v), f)
         dist.destroy_process_group()
     """))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
@@ -42,7 +44,7 @@ def test_gloo_world2_sharding_and_max_reduction(tmp_path):
     pr = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert pr.returncode == 0, pr.stderr[-2000:]
     import json
-    rows = [json.loads(l) for l in pr.stdout.splitlines() if l.startswith("{")]
+    rows = [json.load(open(tmp_path / f"rank{r}.json")) for r in (0, 1)]
     assert sorted(r["rank"] for r in rows) == [0, 1]
     assert rows[0]["first"] != rows[1]["first"]                  # disjoint shards
     for r in rows:
