@@ -9,6 +9,7 @@
  * non-ACGT bytes run through the byte-compare kernel.  There is no CPU path.
  */
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,6 +80,23 @@ struct PinBuf {
     }
 };
 
+/* WFAGPU_TRACE=1: host-side time stamps of a pass (where does the launching thread spend its time) */
+struct HostTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    char buf[512];
+    int len = 0;
+    HostTrace() : on(getenv("WFAGPU_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) { buf[0] = 0; }
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        len += snprintf(buf + len, sizeof(buf) - (size_t)len > 0 ? sizeof(buf) - (size_t)len : 0, " %s=%.0fus", what, us);
+        if (len > (int)sizeof(buf) - 1) len = (int)sizeof(buf) - 1;
+    }
+    ~HostTrace() { if (on) fprintf(stderr, "[wfagpu trace]%s\n", buf); }
+};
+
 enum { CTR_QUEUE = 0, CTR_POOL = 1, CTR_RETRY = 2, CTR_ASCII = 3, CTR_TBQ = 4, CTR_BQ = 5, CTR_WORDS = 8 };
 
 struct LaunchCfg {
@@ -138,6 +156,7 @@ struct Slot {
     size_t packed_words = 0;
     uint32_t max_len = 0;
     uint32_t kt_max = 0;               /* largest |tlen - plen| of the batch */
+    size_t budget_cache = 0;           /* arena budget from the last cudaMemGetInfo (0 = ask again) */
     wfagpu_plan_t plan{};
     wfagpu_batch_stats_t stats{};
     bool have_events = false;
@@ -494,6 +513,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
                        size_t n_items, uint32_t *retry_dev, bool ascii, bool first_pass, bool use_hint,
                        bool *capped_out)
 {
+    HostTrace tr;
     /* step table for the full budget of this pass (cached per slot) */
     const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);
     const int tab_win = plan.band > 0 ? (plan.band_width > 0 ? plan.band_width : 512) : 0;
@@ -576,6 +596,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         rc = choose_cfg(d, plan.x, plan.o, plan.e, n_want, n_min, s.max_len, n_items, ascii, plan.with_cigar != 0, &c);
     }
     if (rc) return rc;
+    tr.mark("cfg");
     /* scores this launch can reach and the decision units they need */
     int d_end = banded ? d_full : d_want;
     uint64_t arena_units = s.tab_arena_units;
@@ -595,10 +616,16 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     /* memory budget of the arenas: a third of the free device memory */
     size_t arena_budget = 0;
     {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        arena_budget = std::max<size_t>((free_b + s.arena.cap * sizeof(uint4)) / 3, (size_t)64 << 20);
+        /* cudaMemGetInfo takes 0.2 - 15 ms on a busy box and would leave the GPU idle between the pack
+         * kernel and this pass: ask only when the answer can have changed (first use, arena grew) */
+        if (s.budget_cache == 0) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            s.budget_cache = std::max<size_t>((free_b + s.arena.cap * sizeof(uint4)) / 3, (size_t)64 << 20);
+        }
+        arena_budget = s.budget_cache;
     }
+    tr.mark("meminfo");
     int period = 0;
     if (c.ckpt) {
         /* Snapshot period: the traceback recomputes ~ score * P cells per pair against ~ score^2 in
@@ -636,6 +663,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     if (s.gring.ensure(groups * gring_elems + 1)) return -1;
     const uint32_t scratch_words = plan.with_cigar ? (uint32_t)((2 * (size_t)d_end + 31) / 16 + 2) : 1;
     const size_t arenas = c.ckpt ? items_per_launch : groups;
+    if (arenas * arena_units + 1 > s.arena.cap) s.budget_cache = 0;      /* the arena grows: re-read the free memory next time */
     if (s.arena.ensure(arenas * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
     const uint32_t band_lo_words = (banded && plan.with_cigar) ? (uint32_t)d_end + 1 : 0;
     if (s.band_lo.ensure(groups * (size_t)band_lo_words + 1)) return -1;
@@ -649,6 +677,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     }
     if (s.pool.ensure(pool_need, true, s.stream)) return -1;
 
+    tr.mark("buffers");
     CK(cudaMemsetAsync(s.counters.p + CTR_RETRY, 0, sizeof(uint32_t), s.stream));
 
     KernelParams kp{};
@@ -724,6 +753,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         const int occ = bound_max_ctas_per_sm(c.A, c.E1, kBoundWarps);
         if (occ < 1) kp.bound = nullptr; else bound_ctas = occ * d->prop.multiProcessorCount;
     }
+    tr.mark("occ");
     for (size_t off = 0; off < n_items; off += items_per_launch) {
         const size_t cnt = std::min(items_per_launch, n_items - off);
         kp.order = order_dev + off;
@@ -748,6 +778,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
             return -1;
         }
         if (time_it) { CK(cudaEventRecord(s.ev[7], s.stream)); s.wf_timed = true; }
+        tr.mark("fwd");
         s.stats.launches += 1;
         if (c.ckpt) {
             /* ring snapshots -> 2-bit ops, a warp per pair */
@@ -761,6 +792,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
             s.stats.launches += 1;
         }
     }
+    tr.mark("tb");
     s.last_d_end = std::max(s.last_d_end, d_end);
     s.text_queued = false;
     return 0;
