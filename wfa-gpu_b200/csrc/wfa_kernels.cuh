@@ -2,14 +2,21 @@
  * wfa_kernels.cuh -- device code of the B200-native gap-affine WFA hot path.
  *
  * Kernels (all integer SIMT work; no tensor cores -- there is no contraction):
- *   pack_kernel      ASCII -> 2-bit, one warp per sequence, 128-bit aligned loads
- *                    (replaces lib/kernels/sequence_packing_kernel.cu:28-116)
- *   wfa_exact_kernel M/I/D offset recurrence + extend + decision bit-planes +
- *                    traceback, one CTA (or one warp) per pair, persistent,
- *                    next pair prefetched with cp.async.bulk (TMA 1-D)
- *                    (replaces lib/kernels/sequence_alignment_kernel.cu:355-688,
- *                     lib/kernels/sequence_distance_kernel.cu:175-423 and the
- *                     device half of utils/cigar.c / lib/align.cu's backtrace slabs)
+ *   pack_kernel          ASCII -> 2-bit, one warp per sequence, 128-bit aligned loads
+ *                        (replaces lib/kernels/sequence_packing_kernel.cu:28-116)
+ *   wfa_bound_kernel     per-pair score upper bound: the recurrence on a re-centred window of 32
+ *                        diagonals, one warp per pair (feeds the exact kernel's pruning)
+ *   wfa_exact_kernel     M/I/D offset recurrence + extend on the score-bound-pruned window, one CTA
+ *                        (or one warp) per pair, persistent, next pair prefetched with
+ *                        cp.async.bulk (TMA 1-D); backtrace state = ring snapshots every P scores
+ *                        (CTA kernels) or one decision byte per cell (warp kernel, large tier)
+ *                        (replaces lib/kernels/sequence_alignment_kernel.cu:355-688,
+ *                         lib/kernels/sequence_distance_kernel.cu:175-423)
+ *   wfa_traceback_kernel ring snapshots -> 2-bit op stream by recomputing the dependency cone under
+ *                        the path, one warp per pair (replaces the bt-word/offload chain of
+ *                        sequence_alignment_kernel.cu and the gather in lib/align.cu)
+ *   wfa_banded_kernel    adaptive band (-B), the reference's heuristic bit for bit
+ *   cigar_text_kernel    op stream + sequences -> CIGAR text on the device (utils/cigar.c)
  *
  * Semantics reproduced from the reference:
  *   k = h - v, offset = h; NULL = -32000 (int16, drifts upward, stays < 0);
