@@ -238,8 +238,11 @@ __device__ __forceinline__ int extend_packed(uint32_t Pa, uint32_t Ta, int plen,
     const uint32_t uv = (uint32_t)v, uh = (uint32_t)h;
     const uint32_t wp = lds_u32(Pa + ((uv >> 3) << 2)) << ((uv & 7u) * 2u);
     const uint32_t wt = lds_u32(Ta + ((uh >> 3) << 2)) << ((uh & 7u) * 2u);
+    const int run = __clz((int)(wp ^ wt)) >> 1;
+    /* at least 9 bases of each window are real: a run of up to 8 needs no further look */
+    if (run <= 8) return off + min(run, rem);
     const int nvalid = 16 - (int)max(uv & 7u, uh & 7u);
-    int e1 = min(__clz((int)(wp ^ wt)) >> 1, rem);
+    int e1 = min(run, rem);
     if (e1 >= nvalid) {
         /* long match (rare off the optimal path): keep going window by window */
         int acc = nvalid;
