@@ -281,6 +281,13 @@ __device__ __forceinline__ int extend_packed_g(const uint32_t *__restrict__ Pw, 
     const int v = off - k, h = off;
     const int rem = min(plen - v, tlen - h);
     if (rem < 0) return kOffNull;
+    {
+        /* common case: the run ends within the 9 bases every window is good for */
+        const uint32_t a = __ldg(Pw + ((uint32_t)v >> 3)) << (((uint32_t)v & 7u) * 2u);
+        const uint32_t b = __ldg(Tw + ((uint32_t)h >> 3)) << (((uint32_t)h & 7u) * 2u);
+        const int run = __clz((int)(a ^ b)) >> 1;
+        if (run <= 8) return off + min(run, rem);
+    }
     int acc = 0;
     while (acc < rem) {
         const uint32_t v2 = (uint32_t)(v + acc), h2 = (uint32_t)(h + acc);
