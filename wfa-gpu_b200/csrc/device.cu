@@ -140,6 +140,8 @@ struct Slot {
     DevBuf<uint32_t> ck_off;           /* arena offset of every ring snapshot (checkpointed traceback) */
     std::vector<uint64_t> h_ck_off;    /* [j] = units used by the snapshots of scores < j * period */
     PinBuf<uint32_t> h_ck32;
+    PinBuf<int32_t> h_bound;           /* re-dispatch: bounds and the retry list on the host */
+    PinBuf<uint32_t> h_retry;
     int ck_key[1] = {-1};              /* period the offsets were built for */
     PinBuf<wfagpu_pair_t> h_pairs;
     PinBuf<uint32_t> h_order;
@@ -254,7 +256,7 @@ extern "C" void wfagpu_device_close_all(void)
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.ascii.release(); s.packed.release(); s.pairs.release(); s.order.release();
             s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
-            s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release(); s.bound.release(); s.ck_off.release(); s.h_ck32.release();
+            s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release(); s.bound.release(); s.ck_off.release(); s.h_ck32.release(); s.h_bound.release(); s.h_retry.release();
             s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release(); s.slots.release(); s.text.release(); s.refs.release(); s.heads.release();
             s.h_text.release(); s.h_refs.release(); s.h_heads.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
@@ -508,29 +510,69 @@ static int ensure_ck_table(Slot &s, const wfagpu_plan_t &plan, int period)
     return 0;
 }
 
+/* Step table for a budget of `max_steps` wavefront steps (cached per slot; host copy in s.h_steps). */
+static int ensure_step_table(Slot &s, const wfagpu_plan_t &plan, int max_steps)
+{
+    const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);
+    const int tab_win = plan.band > 0 ? (plan.band_width > 0 ? plan.band_width : 512) : 0;
+    if (s.tab_key[0] == plan.x && s.tab_key[1] == plan.o && s.tab_key[2] == plan.e && s.tab_key[3] == max_steps &&
+        s.tab_key[4] == tab_win)
+        return 0;
+    if (s.h_steps.ensure((size_t)max_dist + 1)) return -1;
+    CK(cudaStreamSynchronize(s.stream));  /* a previous pass may still be reading the pinned table */
+    uint64_t units = 0;
+    const int de = wfagpu_build_step_table(plan.x, plan.o, plan.e, max_steps, max_dist, tab_win, s.h_steps.p, &units);
+    if (de < 1) return -1;
+    if (s.steps.ensure((size_t)de + 1)) return -1;
+    CK(cudaMemcpyAsync(s.steps.p, s.h_steps.p, (size_t)de * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
+    s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = max_steps; s.tab_key[4] = tab_win;
+    s.tab_d_end = de;
+    s.tab_arena_units = units;
+    s.ck_key[0] = -1;     /* snapshot offsets follow the table */
+    return 0;
+}
+
+/* Score upper bounds only (wfa_bound_kernel) for `n_items` entries of `order_dev`, with a budget of
+ * `max_steps`: the re-dispatch loop uses them to pick a budget that is enough in one go and to prune
+ * that pass per pair.  Leaves the step table of `max_steps` cached. */
+static int run_bound_only(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int max_steps, const uint32_t *order_dev,
+                          size_t n_items)
+{
+    if (ensure_step_table(s, plan, max_steps)) return -1;
+    if (s.bound.ensure(s.n + 1)) return -1;
+    KernelParams kp{};
+    kp.packed = s.packed.p;
+    kp.pairs = s.pairs.p;
+    kp.order = order_dev;
+    kp.n_items = (uint32_t)n_items;
+    kp.steps = s.steps.p;
+    kp.d_end = s.tab_d_end;
+    kp.x = plan.x; kp.o = plan.o; kp.e = plan.e;
+    kp.A = std::max(plan.o + plan.e, plan.x) + 1;
+    kp.E1 = plan.e + 1;
+    kp.bound = s.bound.p;
+    kp.bound_queue = s.counters.p + CTR_BQ;
+    constexpr int kWarps = 8;
+    const int occ = bound_max_ctas_per_sm(kp.A, kp.E1, kWarps);
+    if (occ < 1) return -2;
+    CK(cudaMemsetAsync(s.counters.p + CTR_BQ, 0, sizeof(uint32_t), s.stream));
+    const int ctas = (int)std::min<size_t>((size_t)occ * d->prop.multiProcessorCount, (n_items + kWarps - 1) / kWarps);
+    cudaError_t e = launch_bound(kp, std::max(1, ctas), kWarps, s.stream);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[wfagpu] bound kernel launch failed: %s\n", cudaGetErrorString(e));
+        return -1;
+    }
+    s.stats.launches += 1;
+    return 0;
+}
+
 /* Launch one pass over `n_items` entries of `order_dev`. */
 static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int max_steps, const uint32_t *order_dev,
                        size_t n_items, uint32_t *retry_dev, bool ascii, bool first_pass, bool use_hint,
-                       bool *capped_out)
+                       bool *capped_out, bool have_bounds = false)
 {
     HostTrace tr;
-    /* step table for the full budget of this pass (cached per slot) */
-    const int max_dist = std::min<long long>((long long)max_steps * (std::max(plan.x, plan.o + plan.e) + 1) + 16, 1 << 30);
-    const int tab_win = plan.band > 0 ? (plan.band_width > 0 ? plan.band_width : 512) : 0;
-    if (!(s.tab_key[0] == plan.x && s.tab_key[1] == plan.o && s.tab_key[2] == plan.e && s.tab_key[3] == max_steps &&
-          s.tab_key[4] == tab_win)) {
-        if (s.h_steps.ensure((size_t)max_dist + 1)) return -1;
-        CK(cudaStreamSynchronize(s.stream));  /* a previous pass may still be reading the pinned table */
-        uint64_t units = 0;
-        const int de = wfagpu_build_step_table(plan.x, plan.o, plan.e, max_steps, max_dist, tab_win, s.h_steps.p, &units);
-        if (de < 1) return -1;
-        if (s.steps.ensure((size_t)de + 1)) return -1;
-        CK(cudaMemcpyAsync(s.steps.p, s.h_steps.p, (size_t)de * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
-        s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = max_steps; s.tab_key[4] = tab_win;
-        s.tab_d_end = de;
-        s.tab_arena_units = units;
-        s.ck_key[0] = -1;     /* snapshot offsets follow the table */
-    }
+    if (ensure_step_table(s, plan, max_steps)) return -1;
     const wfagpu_step_t *tab = s.h_steps.p;
     const int d_full = s.tab_d_end;
     int n_full = 0;
@@ -691,8 +733,9 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.bound_queue = s.counters.p + CTR_BQ;
     /* per-pair bounds: first pass of the packed exact path only (a re-dispatched pair never
      * depends on them) */
-    bool use_bound = !banded && !ascii && first_pass && !d->no_bound;
-    if (use_bound && !d->force_bound) {
+    /* have_bounds: s.bound already holds this pass's bounds (run_bound_only) */
+    bool use_bound = !banded && !ascii && (first_pass || have_bounds) && !d->no_bound;
+    if (use_bound && !d->force_bound && !have_bounds) {
         /* Worth it?  With D = d_end - 1 and a typical score m, the launch bound leaves
          * cells(D/m) * m^2 cells per pair (cells(r) = r^2/4 + (1.5r - 1)(1 - r/2), 1 from r = 2 on), the
          * pair's own bound 0.5 * m^2; the bound pass costs ~32 cells per score at ~3x the cost per
@@ -749,7 +792,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     }
     int bound_ctas = 0;
     constexpr int kBoundWarps = 8;
-    if (use_bound) {
+    if (use_bound && !have_bounds) {
         const int occ = bound_max_ctas_per_sm(c.A, c.E1, kBoundWarps);
         if (occ < 1) kp.bound = nullptr; else bound_ctas = occ * d->prop.multiProcessorCount;
     }
@@ -758,7 +801,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         const size_t cnt = std::min(items_per_launch, n_items - off);
         kp.order = order_dev + off;
         kp.n_items = (uint32_t)cnt;
-        if (kp.bound) {
+        if (kp.bound && !have_bounds) {
             CK(cudaMemsetAsync(s.counters.p + CTR_BQ, 0, sizeof(uint32_t), s.stream));
             const int ctas = (int)std::min<size_t>((size_t)bound_ctas, (cnt + kBoundWarps - 1) / kBoundWarps);
             cudaError_t eb = launch_bound(kp, ctas, kBoundWarps, s.stream);
@@ -881,15 +924,51 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     };
     if (read_counters()) return -1;
 
-    /* ---- re-dispatch tier: pairs that outgrew the provisioned rings first get the full
-     * budget, then the wavefront budget doubles until everything finishes ---- */
+    /* Budget oracle: score upper bounds of the pending pairs (bound kernel with the largest budget)
+     * -> the number of wavefront steps that is enough for all of them, 0 if one has no bound. */
+    auto bound_budget = [&](int cur, uint32_t pending, long long *need) -> int {
+        *need = 0;
+        constexpr int kMaxSteps = 60000;
+        int rc = run_bound_only(d, s, plan, kMaxSteps, s.retry[cur].p, pending);
+        if (rc) return rc;
+        if (s.h_bound.ensure(s.n + 1) || s.h_retry.ensure(pending + 1)) return -1;
+        CK(cudaMemcpyAsync(s.h_bound.p, s.bound.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_retry.p, s.retry[cur].p, pending * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        const int d_big = s.tab_d_end;
+        int maxb = 0;
+        for (uint32_t i = 0; i < pending; ++i) {
+            const uint32_t idx = s.h_retry.p[i];
+            if (idx >= s.n) return -1;
+            const int b = s.h_bound.p[idx];
+            if (b >= d_big - 1) return 0;           /* not found within the largest budget: keep doubling */
+            maxb = std::max(maxb, b);
+        }
+        long long steps_needed = 1;                 /* the reference counts the score-0 wavefront as step 1 */
+        for (int dd = 1; dd <= maxb; ++dd) steps_needed += (s.h_steps.p[dd].kind == WFAGPU_STEP_MDI);
+        *need = std::max<long long>(steps_needed + 3, 8);
+        return 0;
+    };
+
+    /* ---- re-dispatch tier: pairs that outgrew the provisioned rings or the budget get, in one go,
+     * the budget their score bounds call for (and are pruned by them); without bounds (banded,
+     * byte-compare pairs) first the full budget, then the budget doubles until everything finishes ---- */
     auto redispatch = [&](bool ascii, int start_steps, bool capped) -> int {
         int cur = 0;
         long long steps = start_steps;
         uint32_t pending = s.h_counters.p[CTR_RETRY];
+        bool oracle_tried = false;
         while (pending > 0) {
             s.stats.redispatched += pending;
             long long next = capped ? steps : std::max<long long>(steps * 2, 64);
+            bool have_bounds = false;
+            if (!oracle_tried && !ascii && plan.band <= 0 && !d->no_bound) {
+                oracle_tried = true;
+                long long need = 0;
+                int rcb = bound_budget(cur, pending, &need);
+                if (rcb < 0) return rcb;
+                if (rcb == 0 && need > 0) { next = need; have_bounds = true; }
+            }
             if (next > 60000) {
                 fprintf(stderr, "[wfagpu] %u pairs need more than %lld wavefront steps; not supported yet\n", pending, steps);
                 return -4;
@@ -897,7 +976,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
             steps = next;
             bool now_capped = false;
             int rc = launch_pass(d, s, plan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, false, false,
-                                 &now_capped);
+                                 &now_capped, have_bounds);
             if (rc) return rc;
             if (read_counters()) return -1;
             if (now_capped && s.h_counters.p[CTR_RETRY] > 0) {
