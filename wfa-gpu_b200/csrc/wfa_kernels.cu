@@ -773,6 +773,17 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const _
  */
 constexpr int kBoundNull = -(1 << 28);
 
+__device__ __forceinline__ int lds_s32(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_32(uint32_t a, int v)
+{
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ KernelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -780,12 +791,14 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = p.x, e = p.e, A = p.A, E1 = p.E1, oe = p.o + p.e;
     const int rows = A + 2 * E1;
-    /* per warp: rows x 32 offsets.  Every row shares one window [wlo, wlo + 31]; diagonal k lives in
-     * slot k & 31, so moving the window only has to clear the slots that change owner. */
-    int *const ring = reinterpret_cast<int *>(smem_raw) + (size_t)warp * (rows * 32);
-    int *const Mr = ring, *const Ir = ring + A * 32, *const Dr = Ir + E1 * 32;
+    /* per warp: rows x 32 int32 offsets (128 bytes per row), explicit shared addresses.  Every row
+     * shares one window [wlo, wlo + 31]; diagonal k lives in slot k & 31, so moving the window only
+     * has to clear the slots that change owner. */
+    const uint32_t ring_sa = smem_u32(smem_raw) + (uint32_t)(warp * rows) * 128u;
+    const uint32_t Mr = ring_sa, Ir = ring_sa + (uint32_t)A * 128u, Dr = Ir + (uint32_t)E1 * 128u;
+    const uint32_t Mend = (uint32_t)A * 128u, Gend = (uint32_t)E1 * 128u;      /* ring sizes in bytes */
     const int Dlaunch = p.d_end - 1;
-    const int slotL = (lane + 31) & 31, slotR = (lane + 1) & 31;
+    const uint32_t me = (uint32_t)lane * 4u, left = (uint32_t)((lane + 31) & 31) * 4u, right = (uint32_t)((lane + 1) & 31) * 4u;
 
     while (true) {
         uint32_t pos = 0;
@@ -798,28 +811,30 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
         const int plen = (int)pr.plen, tlen = (int)pr.tlen, kt = tlen - plen;
         const uint32_t *const Pw = p.packed + pr.p_word;
         const uint32_t *const Tw = p.packed + pr.t_word;
-        for (int r = 0; r < rows; ++r) ring[r * 32 + lane] = kBoundNull;
+        for (int r = 0; r < rows; ++r) sts_32(ring_sa + (uint32_t)r * 128u + me, kBoundNull);
         int wlo = -16;
         int result = Dlaunch;
         {
             const int m = extend_packed_g(Pw, Tw, plen, tlen, 0, 0);
-            if (lane == 0) Mr[0] = m;                       /* score 0: k = 0 sits in slot 0 */
+            __syncwarp();
+            if (lane == 0) sts_32(Mr, m);                    /* score 0: k = 0 sits in slot 0 */
             if (kt == 0 && m == tlen) result = 0;
         }
         __syncwarp();
         if (result != 0) {
-            /* ring rows of the current score and of its sources, stepped with the score */
-            int mc = 0, mx = (A - x) % A, mo = (A - oe) % A, ic = 0, ie = (E1 - e) % E1;
+            /* byte offsets of the ring rows of the current score and of its sources, stepped with the score */
+            uint32_t mc = 0, mx = (uint32_t)((A - x) % A) * 128u, mo = (uint32_t)((A - oe) % A) * 128u;
+            uint32_t ic = 0, ie = (uint32_t)((E1 - e) % E1) * 128u;
             int my_m = kBoundNull, my_k = 0;
             wfagpu_step_t st_next = p.steps[1 < p.d_end ? 1 : 0];
             for (int d = 1; d <= Dlaunch; ++d) {
                 const wfagpu_step_t st = st_next;
                 if (d + 1 < p.d_end) st_next = p.steps[d + 1];
-                if (++mc == A) mc = 0;
-                if (++mx == A) mx = 0;
-                if (++mo == A) mo = 0;
-                if (++ic == E1) ic = 0;
-                if (++ie == E1) ie = 0;
+                mc += 128u; if (mc == Mend) mc = 0;
+                mx += 128u; if (mx == Mend) mx = 0;
+                mo += 128u; if (mo == Mend) mo = 0;
+                ic += 128u; if (ic == Gend) ic = 0;
+                ie += 128u; if (ie == Gend) ie = 0;
                 if ((d & 7) == 0) {
                     /* re-centre on the diagonal with the least sequence left */
                     unsigned key = 0xffffffffu;
@@ -830,7 +845,7 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
                         if (nlo != wlo) {
                             const int k_old = wlo + ((lane - wlo) & 31), k_new = nlo + ((lane - nlo) & 31);
                             if (k_old != k_new)
-                                for (int r = 0; r < rows; ++r) ring[r * 32 + lane] = kBoundNull;
+                                for (int r = 0; r < rows; ++r) sts_32(ring_sa + (uint32_t)r * 128u + me, kBoundNull);
                             wlo = nlo;
                             __syncwarp();
                         }
@@ -841,15 +856,13 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
                 if (st.kind != WFAGPU_STEP_NULL) {
                     const int n = st.n;
                     if (k >= -n && k <= n) {
-                        vM = Mr[mx * 32 + lane] + 1;
+                        vM = lds_s32(Mr + mx + me) + 1;
                         if (st.kind == WFAGPU_STEP_MDI) {
-                            const bool okL = (k != wlo), okR = (k != wlo + 31);
-                            const int moL = okL ? Mr[mo * 32 + slotL] : kBoundNull;
-                            const int ieL = okL ? Ir[ie * 32 + slotL] : kBoundNull;
-                            const int moR = okR ? Mr[mo * 32 + slotR] : kBoundNull;
-                            const int deR = okR ? Dr[ie * 32 + slotR] : kBoundNull;
-                            vI = max(moL, ieL) + 1;
-                            vD = max(moR, deR);
+                            /* neighbours outside the window read as NULL (selects, no branches) */
+                            const int moL = lds_s32(Mr + mo + left), ieL = lds_s32(Ir + ie + left);
+                            const int moR = lds_s32(Mr + mo + right), deR = lds_s32(Dr + ie + right);
+                            vI = (k != wlo) ? max(moL, ieL) + 1 : kBoundNull;
+                            vD = (k != wlo + 31) ? max(moR, deR) : kBoundNull;
                             vM = max(max(vM, vD), vI);
                         }
                         if (vM >= 0) vM = extend_packed_g(Pw, Tw, plen, tlen, k, vM);
@@ -860,9 +873,9 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
                     my_m = vM; my_k = k;
                 }
                 /* the rows being replaced (scores d - A, d - e - 1) are no source of this score */
-                Mr[mc * 32 + lane] = vM;
-                Ir[ic * 32 + lane] = vI;
-                Dr[ic * 32 + lane] = vD;
+                sts_32(Mr + mc + me, vM);
+                sts_32(Ir + ic + me, vI);
+                sts_32(Dr + ic + me, vD);
                 __syncwarp();
                 if (__any_sync(FULL, k == kt && vM == tlen)) { result = d; break; }
             }
