@@ -150,7 +150,8 @@ def test_host_and_device_cigar_text_agree(oracle, monkeypatch):
 @pytest.mark.parametrize("variant", [{"WFAGPU_FORCE_BOUND": "1"}, {"WFAGPU_NO_BOUND": "1"}, {"WFAGPU_NO_CKPT": "1"},
                                      {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_CK_PERIOD": "7"},
                                      {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_CK_PERIOD": "31"},
-                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_NO_HINT": "1"}])
+                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_NO_HINT": "1"},
+                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_ARENA_MB": "8"}])
 def test_kernel_variants_are_bit_exact(variant):
     # per-pair score bounds on/off, ring snapshots vs decision bytes, snapshot periods: one result
     import subprocess, sys as _sys

@@ -1,6 +1,7 @@
 """Run in a subprocess with WFAGPU_* variables that select a kernel variant (read once when the
 device opens): WFAGPU_FORCE_BOUND=1 (per-pair score bounds always), WFAGPU_NO_BOUND=1 (launch
-bound only), WFAGPU_NO_CKPT=1 (decision bytes instead of ring snapshots), WFAGPU_CK_PERIOD=7|15|31.
+bound only), WFAGPU_NO_CKPT=1 (decision bytes instead of ring snapshots), WFAGPU_CK_PERIOD=7|15|31,
+WFAGPU_ARENA_MB=n (snapshot arenas capped: the pass runs in several sub-launches).
 Whatever the variant, scores and CIGARs must be bit-exact vs the oracle, including pairs that
 outgrow the first pass and are re-dispatched."""
 import os, sys
@@ -17,6 +18,8 @@ for pen, cigar in (((2, 3, 1), True), ((2, 3, 1), False), ((5, 3, 2), True), ((4
                           0xB2005000 + rep)
         a.add_sequences("ACGT" * 300, "ACGT" * 300 + "T" * 150)      # long gap: target diagonal far from 0
         a.add_sequences("GATTACA" * 200 + "C" * 211, "GATTACA" * 200)
+        for pp, tt in (("", "ACGT"), ("ACGT", ""), ("ACGT", "ACGT"), ("A", "C"), ("ACGTACGTAC", "TTTTTTTTTT"), ("A", "A" * 40)):
+            a.add_sequences(pp, tt)
         assert a.initialize_parameters(*pen)
         a.options.compute_cigar = cigar
         a.options.max_error = 400          # the 3 kbp / 20 % pairs exceed it: re-dispatched

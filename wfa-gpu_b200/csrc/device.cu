@@ -177,6 +177,7 @@ struct wfagpu_device {
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
     bool no_ckpt = false, no_bound = false, force_bound = false;
     int force_period = 0;
+    int arena_mb = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
     int hint_dist = 0;
     double hint_mean = 0;              /* mean score of the finished pairs of that batch */
@@ -238,6 +239,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->no_ckpt = env_int("WFAGPU_NO_CKPT", 0) != 0;
     d->no_bound = env_int("WFAGPU_NO_BOUND", 0) != 0;
     d->force_bound = env_int("WFAGPU_FORCE_BOUND", 0) != 0;
+    d->arena_mb = env_int("WFAGPU_ARENA_MB", 0);
     d->force_period = env_int("WFAGPU_CK_PERIOD", 0);
     if (d->force_period != 7 && d->force_period != 15 && d->force_period != 31) d->force_period = 0;
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
@@ -660,7 +662,9 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     {
         /* cudaMemGetInfo takes 0.2 - 15 ms on a busy box and would leave the GPU idle between the pack
          * kernel and this pass: ask only when the answer can have changed (first use, arena grew) */
-        if (s.budget_cache == 0) {
+        if (d->arena_mb > 0) {
+            s.budget_cache = (size_t)d->arena_mb << 20;          /* WFAGPU_ARENA_MB: fixed budget (tests) */
+        } else if (s.budget_cache == 0) {
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             s.budget_cache = std::max<size_t>((free_b + s.arena.cap * sizeof(uint4)) / 3, (size_t)64 << 20);
