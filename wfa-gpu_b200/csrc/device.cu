@@ -158,6 +158,7 @@ struct Slot {
     size_t packed_words = 0;
     uint32_t max_len = 0;
     uint32_t kt_max = 0;               /* largest |tlen - plen| of the batch */
+    uint32_t minlen_max = 0;           /* largest min(plen, tlen) of the batch */
     size_t budget_cache = 0;           /* arena budget from the last cudaMemGetInfo (0 = ask again) */
     wfagpu_plan_t plan{};
     wfagpu_batch_stats_t stats{};
@@ -288,12 +289,13 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
     if (s.h_pairs.ensure(n) || s.h_order.ensure(n)) return -1;
     /* packed layout + longest-first schedule */
     size_t words = 0;
-    uint32_t max_len = 0, kt_max = 0;
+    uint32_t max_len = 0, kt_max = 0, minlen_max = 0;
     uint64_t min_sum = ~0ull, max_sum = 0;
     for (size_t i = 0; i < n; ++i) {
         wfagpu_pair_t p = pairs[i];
         const uint64_t sum = (uint64_t)p.plen + p.tlen;
         kt_max = std::max(kt_max, p.plen > p.tlen ? p.plen - p.tlen : p.tlen - p.plen);
+        minlen_max = std::max(minlen_max, std::min(p.plen, p.tlen));
         min_sum = std::min(min_sum, sum);
         max_sum = std::max(max_sum, sum);
         p.p_word = (uint32_t)words;
@@ -312,6 +314,7 @@ extern "C" int wfagpu_device_upload(wfagpu_device_t *d, int slot, const char *as
     s.packed_words = words;
     s.max_len = max_len;
     s.kt_max = kt_max;
+    s.minlen_max = minlen_max;
     if ((uint64_t)min_sum * 8 < (uint64_t)max_sum * 7) {
         /* longest first only pays when the lengths differ by more than ~12 %: for uniform
          * reads the queue order is irrelevant and the sort would dominate the host time */
@@ -584,8 +587,19 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
      * prunes every cell that cannot reach the target diagonal within d_end - 1 (score-bound
      * pruning), so the rings only have to hold max_d min(n_d, kt_max + (d_end - 1 - d) / e). */
     int d_want = d_full;
-    if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e)
+    bool hinted = false;
+    if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e) {
         d_want = (int)std::min<long long>((long long)d->hint_dist + d->hint_dist / 12 + 8, d_full - 1) + 1;
+        hinted = d_want < d_full;
+    }
+    /* no pair of the batch can score more than substitutions all along the shorter sequence plus one
+     * gap for the length difference: a generous -e (or a stale hint) does not widen the rings */
+    int d_reach = d_full;                    /* scores beyond this cannot occur in this batch */
+    if (plan.band <= 0) {
+        const long long cap = (long long)plan.x * s.minlen_max + plan.o + (long long)plan.e * s.kt_max + 2;
+        if (cap < d_reach) d_reach = (int)std::max<long long>(cap, 2);
+        if (d_reach < d_want) d_want = d_reach;
+    }
     const int pen_e = plan.e;
     const long long kt_max = s.kt_max;
     auto n_need = [&](int d_end) -> int {
@@ -605,7 +619,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     int n_want = plan.band > 0 ? n_full : n_need(d_want);
     /* with a hint, rings for hint + 3 % are enough for (almost) every pair */
     int n_min = n_want;
-    if (d_want < d_full && plan.band <= 0)
+    if (hinted && plan.band <= 0)
         n_min = std::min(n_want, n_need((int)std::min<long long>((long long)d->hint_dist + d->hint_dist / 32 + 4, d_full - 1) + 1));
     const bool banded = plan.band > 0;
     LaunchCfg c{};
@@ -655,7 +669,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         }
         arena_units = d_end < d_full ? tab[d_end].row_off : s.tab_arena_units;
     }
-    *capped_out = d_end < d_full;
+    *capped_out = d_end < d_reach;          /* provisioned below what the budget (and the lengths) allow */
 
     /* memory budget of the arenas: a third of the free device memory */
     size_t arena_budget = 0;
@@ -677,7 +691,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         /* Snapshot period: the traceback recomputes ~ score * P cells per pair against ~ score^2 in
          * the forward pass, the snapshots take ~ 1/P of the cells: short periods for low scores,
          * longer ones when memory is tight. */
-        const int d_expect = (d_want < d_full) ? std::min(d_end, d->hint_dist + 1) : d_end;
+        const int d_expect = hinted ? std::min(d_end, d->hint_dist + 1) : d_end;
         period = d->force_period ? d->force_period : (d_expect >= 3000 ? 31 : 15);   /* measured on B200: shorter never wins */
         for (;;) {
             if (ensure_ck_table(s, plan, period)) return -1;
@@ -744,8 +758,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
          * cells(D/m) * m^2 cells per pair (cells(r) = r^2/4 + (1.5r - 1)(1 - r/2), 1 from r = 2 on), the
          * pair's own bound 0.5 * m^2; the bound pass costs ~32 cells per score at ~3x the cost per
          * cell (measured on B200: ~240 against ~2.75 warp instructions). */
-        const bool hinted = d_want < d_full && d->hint_mean > 0;
-        const double m = hinted ? d->hint_mean : 0.5 * (d_end - 1);
+        const double m = (hinted && d->hint_mean > 0) ? d->hint_mean : 0.5 * (d_end - 1);
         const double r = std::min(2.0, std::max(1.0, (d_end - 1) / std::max(1.0, m)));
         const double cells = r * r / 4 + (1.5 * r - 1) * (1 - r / 2);
         use_bound = (cells - 0.5) * m > 130.0;

@@ -345,7 +345,7 @@ constexpr uint32_t kSchedBytes = 2u * kSchedBlock * (uint32_t)sizeof(StepRec);
  * recomputes the offsets it needs on the dependency cone below the cell it stands on
  * (model + proof of equivalence: oracle/kernel_model.c, km_align_pair_ckpt). */
 template <bool WARP, bool ASCII, bool BT, typename R, bool CKPT>
-__global__ void __launch_bounds__(WARP ? 256 : 1024, 1) wfa_exact_kernel(const __grid_constant__ KernelParams p)
+__global__ void __launch_bounds__(WARP ? 256 : 1024, WARP ? 4 : 1) wfa_exact_kernel(const __grid_constant__ KernelParams p)
 {
     static_assert(!CKPT || (BT && !WARP && R::kElem == 2), "checkpointed traceback: CTA groups with shared-memory rings");
     using G = Group<WARP>;
