@@ -853,9 +853,10 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
                 }
                 const int k = wlo + ((lane - wlo) & 31);
                 int vM = kBoundNull, vI = kBoundNull, vD = kBoundNull;
-                if (st.kind != WFAGPU_STEP_NULL) {
+                if (st.kind != WFAGPU_STEP_NULL) {                 /* uniform */
                     const int n = st.n;
-                    if (k >= -n && k <= n) {
+                    const bool in = (k >= -n && k <= n);
+                    if (in) {
                         vM = lds_s32(Mr + mx + me) + 1;
                         if (st.kind == WFAGPU_STEP_MDI) {
                             /* neighbours outside the window read as NULL (selects, no branches) */
@@ -865,11 +866,52 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
                             vD = (k != wlo + 31) ? max(moR, deR) : kBoundNull;
                             vM = max(max(vM, vD), vI);
                         }
-                        if (vM >= 0) vM = extend_packed_g(Pw, Tw, plen, tlen, k, vM);
-                        if (vM < 0) vM = kBoundNull;
-                        if (vI < 0) vI = kBoundNull;
-                        if (vD < 0) vD = kBoundNull;
                     }
+                    /* extend: a run of up to 8 bases is settled by the lane itself; the one or two lanes on
+                     * the alignment path have long runs, and instead of dragging the warp through their
+                     * serial loops the whole warp compares 256 bases of such a run per round */
+                    const int ev = vM - k, eh = vM;
+                    int rem = -1;
+                    bool lng = false;
+                    if (in && vM >= 0) {
+                        rem = min(plen - ev, tlen - eh);
+                        if (rem >= 0) {
+                            const uint32_t a = __ldg(Pw + ((uint32_t)ev >> 3)) << (((uint32_t)ev & 7u) * 2u);
+                            const uint32_t b = __ldg(Tw + ((uint32_t)eh >> 3)) << (((uint32_t)eh & 7u) * 2u);
+                            const int run = __clz((int)(a ^ b)) >> 1;
+                            if (run <= 8) vM = eh + min(run, rem); else lng = true;
+                        } else {
+                            vM = kBoundNull;
+                        }
+                    }
+                    unsigned need = __ballot_sync(FULL, lng);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int v0 = __shfl_sync(FULL, ev, src), h0 = __shfl_sync(FULL, eh, src);
+                        const int rem0 = __shfl_sync(FULL, rem, src);
+                        int total = rem0;
+                        for (int base = 0; base < rem0; base += 256) {
+                            const int start = base + 8 * lane;
+                            int eq = 0;
+                            if (start < rem0) {
+                                const uint32_t pv = (uint32_t)(v0 + start), ph = (uint32_t)(h0 + start);
+                                const uint32_t a = __ldg(Pw + (pv >> 3)) << ((pv & 7u) * 2u);
+                                const uint32_t b = __ldg(Tw + (ph >> 3)) << ((ph & 7u) * 2u);
+                                eq = min(min(__clz((int)(a ^ b)) >> 1, 8), rem0 - start);
+                            }
+                            const unsigned stop = __ballot_sync(FULL, eq < 8);
+                            if (stop) {
+                                const int f = __ffs(stop) - 1;
+                                total = base + 8 * f + __shfl_sync(FULL, eq, f);
+                                break;
+                            }
+                        }
+                        if (lane == src) vM = eh + min(total, rem);
+                    }
+                    if (vM < 0) vM = kBoundNull;
+                    if (vI < 0) vI = kBoundNull;
+                    if (vD < 0) vD = kBoundNull;
                     my_m = vM; my_k = k;
                 }
                 /* the rows being replaced (scores d - A, d - e - 1) are no source of this score */
