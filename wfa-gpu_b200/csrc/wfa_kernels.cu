@@ -301,6 +301,57 @@ __device__ __forceinline__ int extend_packed_g(const uint32_t *__restrict__ Pw, 
     return off + min(acc, rem);
 }
 
+/* extend for the warp-per-pair kernels, called by all 32 lanes together: a lane that `want`s it gets
+ * off + (common prefix of P[off-k ..] and T[off ..]), or null_v outside the sequences; the others get
+ * `off` back.  A run of up to 8 bases is settled by the lane itself.  The one or two lanes on the
+ * alignment path have long runs, and instead of dragging the warp through their serial loops the whole
+ * warp compares 256 bases of such a run per round (8 per lane: every window has >= 9 real bases). */
+__device__ __forceinline__ int warp_extend_packed(const uint32_t *__restrict__ Pw, const uint32_t *__restrict__ Tw,
+                                                  int plen, int tlen, bool want, int k, int off, int null_v, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int ev = off - k, eh = off;
+    int rem = -1, res = off;
+    bool lng = false;
+    if (want) {
+        rem = min(plen - ev, tlen - eh);
+        if (rem >= 0) {
+            const uint32_t a = __ldg(Pw + ((uint32_t)ev >> 3)) << (((uint32_t)ev & 7u) * 2u);
+            const uint32_t b = __ldg(Tw + ((uint32_t)eh >> 3)) << (((uint32_t)eh & 7u) * 2u);
+            const int run = __clz((int)(a ^ b)) >> 1;
+            if (run <= 8) res = eh + min(run, rem); else lng = true;
+        } else {
+            res = null_v;
+        }
+    }
+    unsigned need = __ballot_sync(FULL, lng);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int v0 = __shfl_sync(FULL, ev, src), h0 = __shfl_sync(FULL, eh, src);
+        const int rem0 = __shfl_sync(FULL, rem, src);
+        int total = rem0;
+        for (int base = 0; base < rem0; base += 256) {
+            const int start = base + 8 * lane;
+            int eq = 0;
+            if (start < rem0) {
+                const uint32_t pv = (uint32_t)(v0 + start), ph = (uint32_t)(h0 + start);
+                const uint32_t a = __ldg(Pw + (pv >> 3)) << ((pv & 7u) * 2u);
+                const uint32_t b = __ldg(Tw + (ph >> 3)) << ((ph & 7u) * 2u);
+                eq = min(min(__clz((int)(a ^ b)) >> 1, 8), rem0 - start);
+            }
+            const unsigned stop = __ballot_sync(FULL, eq < 8);
+            if (stop) {
+                const int f = __ffs(stop) - 1;
+                total = base + 8 * f + __shfl_sync(FULL, eq, f);
+                break;
+            }
+        }
+        if (lane == src) res = eh + min(total, rem);
+    }
+    return res;
+}
+
 /* Score-bound pruning window of one score: the diagonals of [-n, n] within q = (Dmax - d) / e of
  * the target diagonal.  When none is (an all-NULL step) the window is the clamped full range, so
  * that the rows still read as NULL wherever a later score may look.  Returns whether any cell is
@@ -867,48 +918,7 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
                             vM = max(max(vM, vD), vI);
                         }
                     }
-                    /* extend: a run of up to 8 bases is settled by the lane itself; the one or two lanes on
-                     * the alignment path have long runs, and instead of dragging the warp through their
-                     * serial loops the whole warp compares 256 bases of such a run per round */
-                    const int ev = vM - k, eh = vM;
-                    int rem = -1;
-                    bool lng = false;
-                    if (in && vM >= 0) {
-                        rem = min(plen - ev, tlen - eh);
-                        if (rem >= 0) {
-                            const uint32_t a = __ldg(Pw + ((uint32_t)ev >> 3)) << (((uint32_t)ev & 7u) * 2u);
-                            const uint32_t b = __ldg(Tw + ((uint32_t)eh >> 3)) << (((uint32_t)eh & 7u) * 2u);
-                            const int run = __clz((int)(a ^ b)) >> 1;
-                            if (run <= 8) vM = eh + min(run, rem); else lng = true;
-                        } else {
-                            vM = kBoundNull;
-                        }
-                    }
-                    unsigned need = __ballot_sync(FULL, lng);
-                    while (need) {
-                        const int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int v0 = __shfl_sync(FULL, ev, src), h0 = __shfl_sync(FULL, eh, src);
-                        const int rem0 = __shfl_sync(FULL, rem, src);
-                        int total = rem0;
-                        for (int base = 0; base < rem0; base += 256) {
-                            const int start = base + 8 * lane;
-                            int eq = 0;
-                            if (start < rem0) {
-                                const uint32_t pv = (uint32_t)(v0 + start), ph = (uint32_t)(h0 + start);
-                                const uint32_t a = __ldg(Pw + (pv >> 3)) << ((pv & 7u) * 2u);
-                                const uint32_t b = __ldg(Tw + (ph >> 3)) << ((ph & 7u) * 2u);
-                                eq = min(min(__clz((int)(a ^ b)) >> 1, 8), rem0 - start);
-                            }
-                            const unsigned stop = __ballot_sync(FULL, eq < 8);
-                            if (stop) {
-                                const int f = __ffs(stop) - 1;
-                                total = base + 8 * f + __shfl_sync(FULL, eq, f);
-                                break;
-                            }
-                        }
-                        if (lane == src) vM = eh + min(total, rem);
-                    }
+                    vM = warp_extend_packed(Pw, Tw, plen, tlen, in && vM >= 0, k, vM, kBoundNull, lane);
                     if (vM < 0) vM = kBoundNull;
                     if (vI < 0) vI = kBoundNull;
                     if (vD < 0) vD = kBoundNull;
@@ -1031,21 +1041,28 @@ __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constan
             if (lane < Rr) { const wfagpu_step_t t = p.steps[c + 1 + lane]; my_nk = (uint32_t)t.n | ((uint32_t)t.kind << 16); }
             __syncwarp();
             /* ---- recompute levels 1 .. Rr on the cone ---- */
+            /* (Dmax - (c + i)) = q * e + r and the row offsets are stepped with the level */
+            int pq = (Dmax - c) / e, prr = (Dmax - c) % e;
+            uint32_t rowC = 2u * (uint32_t)(L0 * WP);
             for (int i = 1; i <= Rr; ++i) {
                 const uint32_t nk = __shfl_sync(FULL, my_nk, i - 1);
                 const int n_i = (int)(nk & 0xffffu), kind_i = (int)(nk >> 16);
                 const int half = Rr - i;
+                if (prr == 0) { prr = e - 1; --pq; } else --prr;
                 int lo_i, hi_i;
-                if (!prune_window(n_i, kt, (Dmax - (c + i)) / e, p.n_cap, lo_i, hi_i)) { lo_i = 1; hi_i = 0; }
-                const uint32_t rowC = 2u * (uint32_t)((i + L0) * WP);
-                const uint32_t rowX = 2u * (uint32_t)((i - x + L0) * WP);
-                const uint32_t rowO = 2u * (uint32_t)((i - oe + L0) * WP);
-                const uint32_t rowE = 2u * (uint32_t)((i - e + L0) * WP);
-                for (int j = P - half + lane; j <= P + half; j += 32) {
+                if (!prune_window(n_i, kt, pq, p.n_cap, lo_i, hi_i)) { lo_i = 1; hi_i = 0; }
+                rowC += 2u * (uint32_t)WP;
+                const uint32_t rowX = rowC - 2u * (uint32_t)(x * WP);
+                const uint32_t rowO = rowC - 2u * (uint32_t)(oe * WP);
+                const uint32_t rowE = rowC - 2u * (uint32_t)(e * WP);
+                for (int j0 = P - half; j0 <= P + half; j0 += 32) {          /* uniform trip count */
+                    const int j = j0 + lane;
+                    const bool act = j <= P + half;
                     const int k = kc - P + j;
                     const uint32_t cj = 2u * (uint32_t)j;
                     int vM = NULLV, vI = NULLV, vD = NULLV;
-                    if (kind_i != WFAGPU_STEP_NULL && k >= lo_i && k <= hi_i) {
+                    const bool live = act && kind_i != WFAGPU_STEP_NULL && k >= lo_i && k <= hi_i;
+                    if (live) {
                         if (kind_i == WFAGPU_STEP_M) {
                             vM = lds_s16(sM + rowX + cj) + 1;
                         } else {
@@ -1053,11 +1070,17 @@ __global__ void __launch_bounds__(256) wfa_traceback_kernel(const __grid_constan
                             vD = max(lds_s16(sM + rowO + cj + 2u), lds_s16(sD + rowE + cj + 2u));
                             vM = max(max(lds_s16(sM + rowX + cj) + 1, vD), vI);
                         }
-                        if (vM >= 0) vM = extend(k, vM);
                     }
-                    sts_16(sM + rowC + cj, vM);
-                    sts_16(sI + rowC + cj, vI);
-                    sts_16(sD + rowC + cj, vD);
+                    if constexpr (ASCII) {
+                        if (live && vM >= 0) vM = extend(k, vM);
+                    } else {
+                        vM = warp_extend_packed(Pw, Tw, plen, tlen, live && vM >= 0, k, vM, NULLV, lane);
+                    }
+                    if (act) {
+                        sts_16(sM + rowC + cj, vM);
+                        sts_16(sI + rowC + cj, vI);
+                        sts_16(sD + rowC + cj, vD);
+                    }
                 }
                 __syncwarp();
             }
