@@ -159,3 +159,26 @@ def test_kernel_variants_are_bit_exact(variant):
     pr = subprocess.run([_sys.executable, os.path.join(root, "tests", "variant_check.py")], env=dict(os.environ, **variant),
                         capture_output=True, text=True, timeout=1500)
     assert pr.returncode == 0, pr.stdout[-3000:] + pr.stderr[-3000:]
+
+
+def test_headline_batch_at_full_size(oracle, refcpu):
+    # BASELINE's headline configuration at bench.py's full size (8192 x 10 kbp, 5 %, -e 3000, CIGAR),
+    # checked through properties that do not need the oracle on every pair:
+    #   * every score equals the unmodified reference CPU WFA (all pairs),
+    #   * every CIGAR is an alignment of its two sequences whose gap-affine cost is that score,
+    #   * a second call (provisioned from the first one's scores: per-pair bounds, tighter rings,
+    #     another CTA per SM) returns byte-identical results,
+    #   * a sample equals the oracle's CIGAR text byte for byte.
+    a = run([(8192, 10000, 0.05, 0.05)], (2, 3, 1), True, max_error=3000, batch=4096, seed=0xB2000004)
+    errs, cigs = a.errors(), a.cigars()
+    pairs = [a.pair(i) for i in range(a.num_pairs)]
+    ref, _ = refcpu.align_batch([p for p, _ in pairs], [t for _, t in pairs], 2, 3, 1, cigar=False)
+    assert errs == ref
+    for (p, t), s, c in zip(pairs, errs, cigs):
+        assert oracle.cigar_score(p, t, c, 2, 3, 1) == s
+    a.reset_results()
+    a.align()
+    assert a.errors() == errs and a.cigars() == cigs
+    for i in range(0, a.num_pairs, 683):
+        r = oracle.align(pairs[i][0], pairs[i][1], 2, 3, 1, 3000)
+        assert (errs[i], cigs[i]) == (r["distance"], r["cigar"])
