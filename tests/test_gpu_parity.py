@@ -182,3 +182,21 @@ def test_headline_batch_at_full_size(oracle, refcpu):
     for i in range(0, a.num_pairs, 683):
         r = oracle.align(pairs[i][0], pairs[i][1], 2, 3, 1, 3000)
         assert (errs[i], cigs[i]) == (r["distance"], r["cigar"])
+
+
+@pytest.mark.parametrize("pen", [(4, 6, 2), (3, 1, 4), (2, 10, 5), (5, 3, 2)])
+def test_long_reads_with_gap_extension_above_one(oracle, refcpu, pen):
+    # e > 1 exercises the quotient of the score-bound pruning ((Dmax - d) / e), the reachability bound
+    # and the snapshot geometry at sizes where bounds, hints and re-provisioning are all active:
+    # scores vs the unmodified reference CPU WFA, CIGARs must be alignments of exactly that cost,
+    # and a sample must equal the oracle's CIGAR text.
+    a = run([(1536, 5000, 0.02, 0.08)], pen, True, max_error=6000, batch=512, seed=0xB2000040 + pen[2])
+    errs, cigs = a.errors(), a.cigars()
+    pairs = [a.pair(i) for i in range(a.num_pairs)]
+    ref, _ = refcpu.align_batch([p for p, _ in pairs], [t for _, t in pairs], *pen, cigar=False)
+    assert errs == ref
+    for (p, t), s, c in zip(pairs, errs, cigs):
+        assert oracle.cigar_score(p, t, c, *pen) == s
+    for i in range(0, a.num_pairs, 191):
+        r = oracle.align(pairs[i][0], pairs[i][1], *pen, 6000)
+        assert (errs[i], cigs[i]) == (r["distance"], r["cigar"])
