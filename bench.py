@@ -302,7 +302,10 @@ def run_ours(args):
                     "nominal_instr_per_cell": 64,
                     "achieved": round(cells * 64 / (k_ms / 1e3) / 1e12, 3), "peak": round(int_peak / 1e12, 3),
                     "unit": "T thread-instr/s", "frac": round(cells * 64 / (k_ms / 1e3) / int_peak, 4),
-                    "gcells_per_s": round(cells / (k_ms / 1e3) / 1e9, 3)}
+                    "gcells_per_s": round(cells / (k_ms / 1e3) / 1e9, 3),
+                    # SURVEY 8(d) defines the work unit with the reference's growth model (cells_without_pruning):
+                    # the same time against that work -- above 1 means fewer cells than the reference computes
+                    "frac_of_reference_work": round(cells_unpruned * 64 / (k_ms / 1e3) / int_peak, 4)}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
