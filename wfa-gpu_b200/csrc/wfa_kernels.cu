@@ -1530,9 +1530,22 @@ __device__ __forceinline__ uint32_t put_run(char *dst, uint32_t pos, uint32_t re
 {
     /* "%d%c" (insert_ops, utils/cigar.c:31-61); nothing for an empty run */
     if (rep == 0) return pos;
-    uint32_t div = 1;
-    while (rep / div >= 10u) div *= 10u;
-    for (; div; div /= 10u) dst[pos++] = (char)('0' + (rep / div) % 10u);
+    if (rep < 10u) {                                   /* almost every op run, half of the match runs */
+        dst[pos++] = (char)('0' + rep);
+    } else if (rep < 100u) {                           /* constant divisors: multiply-shift, no division */
+        const uint32_t q = rep / 10u;
+        dst[pos++] = (char)('0' + q);
+        dst[pos++] = (char)('0' + (rep - 10u * q));
+    } else if (rep < 1000u) {
+        const uint32_t h = rep / 100u, r = rep - 100u * h, q = r / 10u;
+        dst[pos++] = (char)('0' + h);
+        dst[pos++] = (char)('0' + q);
+        dst[pos++] = (char)('0' + (r - 10u * q));
+    } else {
+        uint32_t div = 1000u;
+        while (rep / div >= 10u) div *= 10u;
+        for (; div; div /= 10u) dst[pos++] = (char)('0' + (rep / div) % 10u);
+    }
     dst[pos++] = op;
     return pos;
 }
