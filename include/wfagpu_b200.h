@@ -40,7 +40,8 @@ typedef struct {
  * size it).  `arena_units` receives the number of 16-byte decision units one
  * alignment can write.  Budget rule = reference: MDI steps stop once
  * steps >= max_steps-1 (sequence_alignment_kernel.cu:584, steps starts at 1).
- * banded_win == 0: exact kernels (n = computed half width, row_off = bit-plane row);
+ * banded_win == 0: exact kernels (n = computed half width, row_off = decision-byte row of the
+ * warp-per-pair and large-tier kernels; the CTA kernels keep ring snapshots instead, laid out by the device layer);
  * banded_win  > 0: banded kernels (n = number of M/I/D steps so far, rows of
  * ceil(win/16) units).  A decision row holds one byte per diagonal. */
 int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist, int banded_win,
@@ -126,10 +127,10 @@ int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const wfagpu_pla
                         int resident);
 int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wfagpu_pair_out_t *out,
                            uint32_t **ops, size_t *ops_used, uint32_t *pair_flags);
-/* Waits for the slot's stream; event-timed durations of the last pack and first
- * alignment launch (milliseconds). */
+/* Waits for the slot's stream; event-timed durations (milliseconds) of the pack kernel and of the
+ * first pass of the alignment: score bounds + wavefronts + traceback + CIGAR text. */
 int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, float *ms_align);
-/* After wfagpu_device_download: CIGAR text emitted on the device (one thread per pair, the
+/* After wfagpu_device_download: CIGAR text emitted on the device (one warp per pair, the
  * reference's exact format) and compacted; `*text` / `*refs` point into pinned memory owned by
  * the slot.  Replaces the host loop over recover_cigar_affine (utils/wfa_cpu.c:88-107). */
 int wfagpu_device_download_text(wfagpu_device_t *d, int slot, size_t n, const char **text, size_t *text_bytes,
