@@ -410,7 +410,11 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
         c->ckpt = ck;
         int best_k = 0, stages = 1, n_cap = n_want;
         size_t smem = 0;
-        const int kmax = d->force_ctas_per_sm ? d->force_ctas_per_sm : 6;
+        /* CTA size follows the average width of the pruned wavefront (~ n_want): a quarter of it, 64..192
+         * threads, and as many CTAs per SM as give ~960 threads (measured on B200: 10 kbp / 5 % is flat from
+         * 128 to 192 threads at 5 CTAs; 1 kbp / 10 % runs 17.2 ms with 6 x 160 and 13.1 ms with 15 x 64) */
+        const int t_pref = std::min(192, std::max(64, (((n_want + 3) / 4) + 31) & ~31));
+        const int kmax = d->force_ctas_per_sm ? d->force_ctas_per_sm : std::min(16, std::max(1, 960 / t_pref));
         /* n_min <= n_want: the rings may be provisioned below n_want (down to n_min) when that buys
          * another resident CTA -- the few pairs that then outgrow them are re-dispatched */
         n_min = std::max(1, std::min(n_min, n_want));
