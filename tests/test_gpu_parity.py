@@ -200,3 +200,22 @@ def test_long_reads_with_gap_extension_above_one(oracle, refcpu, pen):
     for i in range(0, a.num_pairs, 191):
         r = oracle.align(pairs[i][0], pairs[i][1], *pen, 6000)
         assert (errs[i], cigs[i]) == (r["distance"], r["cigar"])
+
+
+def test_banded_pairs_over_budget_are_finished_by_the_exact_kernels(oracle):
+    # The reference hands pairs the banded kernel did not finish to the CPU WFA; here they are
+    # re-dispatched on the GPU through the exact kernels (a band that lost the alignment does not find
+    # it again with a larger budget).  Pairs the banded pass finishes keep the heuristic's result.
+    pen, band, window, budget = (2, 3, 1), 10, 64, 120
+    a = run_banded([(200, 1000, 0.02, 0.12)], pen, True, band, window, budget)
+    n_exact = 0
+    for i in range(a.num_pairs):
+        p, t = a.pair(i)
+        r = oracle.align(p, t, *pen, budget, band=band, window=window, cigar=True)
+        if not r["finished"]:
+            r = oracle.align(p, t, *pen, 8000, cigar=True)       # exact
+            n_exact += 1
+        assert r["finished"]
+        assert (a.error(i), a.cigar(i)) == (r["distance"], r["cigar"])
+    assert 10 < n_exact < a.num_pairs
+    assert a.run_stats()["redispatched"] == n_exact

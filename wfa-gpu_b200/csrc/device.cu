@@ -945,12 +945,17 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     };
     if (read_counters()) return -1;
 
+    /* Re-dispatched pairs always run the exact kernels: a band that lost the alignment does not find it
+     * again with a larger budget (the reference hands such pairs to the CPU WFA, utils/wfa_cpu.c:30-86). */
+    wfagpu_plan_t replan = plan;
+    replan.band = 0;
+
     /* Budget oracle: score upper bounds of the pending pairs (bound kernel with the largest budget)
      * -> the number of wavefront steps that is enough for all of them, 0 if one has no bound. */
     auto bound_budget = [&](int cur, uint32_t pending, long long *need) -> int {
         *need = 0;
         constexpr int kMaxSteps = 60000;
-        int rc = run_bound_only(d, s, plan, kMaxSteps, s.retry[cur].p, pending);
+        int rc = run_bound_only(d, s, replan, kMaxSteps, s.retry[cur].p, pending);
         if (rc) return rc;
         if (s.h_bound.ensure(s.n + 1) || s.h_retry.ensure(pending + 1)) return -1;
         CK(cudaMemcpyAsync(s.h_bound.p, s.bound.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
@@ -983,7 +988,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
             s.stats.redispatched += pending;
             long long next = capped ? steps : std::max<long long>(steps * 2, 64);
             bool have_bounds = false;
-            if (!oracle_tried && !ascii && plan.band <= 0 && !d->no_bound) {
+            if (!oracle_tried && !ascii && !d->no_bound) {
                 oracle_tried = true;
                 long long need = 0;
                 int rcb = bound_budget(cur, pending, &need);
@@ -996,7 +1001,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
             }
             steps = next;
             bool now_capped = false;
-            int rc = launch_pass(d, s, plan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, false, false,
+            int rc = launch_pass(d, s, replan, (int)steps, s.retry[cur].p, pending, s.retry[cur ^ 1].p, ascii, false, false,
                                  &now_capped, have_bounds);
             if (rc) return rc;
             if (read_counters()) return -1;
