@@ -219,3 +219,36 @@ def test_banded_pairs_over_budget_are_finished_by_the_exact_kernels(oracle):
         assert (a.error(i), a.cigar(i)) == (r["distance"], r["cigar"])
     assert 10 < n_exact < a.num_pairs
     assert a.run_stats()["redispatched"] == n_exact
+
+
+def test_non_acgt_pairs_match_cpu_wfa_scores(oracle, refcpu):
+    # Pairs the packer flags (an 'N' in either sequence, sequence_packing_kernel.cu:54-76) go through the
+    # byte-compare kernels, as the reference sends them to its CPU WFA: same byte-equality semantics, so
+    # the same optimal score; the CIGAR must be an alignment of that cost.  (Other non-ACGT bytes are not
+    # flagged by the reference and are 2-bit encoded as (c & 6) >> 1 on its GPU path -- and here.)
+    # Mixed with clean pairs in one batch, small budget so that some flagged pairs are also re-dispatched.
+    import random
+    rng = random.Random(77)
+    a = synth_aligner([(300, 800, 0.02, 0.10), (40, 3000, 0.05, 0.05)], 0xB2000077)
+    pairs = [a.pair(i) for i in range(a.num_pairs)]
+    b = wfagpu.Aligner()
+    dirty = []
+    for i, (p, t) in enumerate(pairs):
+        if i % 3 == 0:
+            p, t = list(p), list(t)
+            for s in (p, t):
+                for _ in range(rng.randint(1, 6)):
+                    s[rng.randrange(len(s))] = "N"
+            p, t = "".join(p), "".join(t)
+            dirty.append(i)
+        assert b.add_sequences(p, t)
+    assert b.initialize_parameters(2, 3, 1)
+    b.options.compute_cigar = True
+    b.options.max_error = 150
+    b.align()
+    bp = [b.pair(i) for i in range(b.num_pairs)]
+    ref, _ = refcpu.align_batch([p for p, _ in bp], [t for _, t in bp], 2, 3, 1, cigar=False)
+    assert b.errors() == ref
+    for i, (p, t) in enumerate(bp):
+        assert oracle.cigar_score(p, t, b.cigar(i), 2, 3, 1) == ref[i]
+    assert b.run_stats()["ascii_pairs"] >= len([i for i in dirty if oracle.has_N(bp[i][0]) or oracle.has_N(bp[i][1])])
