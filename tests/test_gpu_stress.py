@@ -17,3 +17,9 @@ def test_randomised_sweep(env):
                         env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert pr.returncode == 0, pr.stdout[-2000:] + pr.stderr[-2000:]
     assert "mismatches=0" in pr.stdout
+
+
+def test_extreme_shapes():
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "extreme_check.py")], capture_output=True, text=True,
+                        timeout=900)
+    assert pr.returncode == 0, pr.stdout[-2000:] + pr.stderr[-2000:]
