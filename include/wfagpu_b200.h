@@ -205,6 +205,13 @@ long wfagpu_read_fasta_files(wfagpu_aligner_t *aligner, const char *query_path, 
 bool wfagpu_check_result(const char *pattern, size_t plen, const char *text, size_t tlen,
                          affine_penalties_t pen, unsigned int error, const char *cigar);
 
+/* The reference library's generic validators, same names and argument order (text first;
+ * utils/verification.h:37-49): the CIGAR is a global alignment of (pattern, text) / its gap-affine
+ * cost equals `distance`. */
+bool check_cigar_edit(const char *text, const char *pattern, const int tlen, const int plen, const char *curr_cigar);
+bool check_affine_distance(const char *text, const char *pattern, const int tlen, const int plen, const int distance,
+                           const affine_penalties_t penalties, const char *cigar);
+
 /* Deterministic synthetic pairs (text uniform over ACGT, pattern =
  * text with ceil(L*err) edits, each uniformly mismatch / 1-base deletion /
  * 1-base insertion; splitmix64 seeded).  Appends n pairs to the aligner. */

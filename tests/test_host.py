@@ -199,3 +199,23 @@ def test_check_result(lib, oracle):
     assert not lib.wfagpu_check_result(p, len(p), t, len(t), pen, r["distance"] + 1, r["cigar"].encode())
     assert not lib.wfagpu_check_result(p, len(p), t, len(t), pen, 0, b"9M")
     assert not lib.wfagpu_check_result(p, len(p), t, len(t), pen, 0, b"garbage")
+
+
+def test_reference_validator_names(lib, oracle):
+    # check_cigar_edit / check_affine_distance: the reference library's generic validators, exported under
+    # the same names with the same argument order (text first; utils/verification.h:37-49)
+    import ctypes as C
+    lib.check_cigar_edit.restype = C.c_bool
+    lib.check_cigar_edit.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+    lib.check_affine_distance.restype = C.c_bool
+    lib.check_affine_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, wfagpu.AffinePenalties,
+                                          C.c_char_p]
+    pen = wfagpu.AffinePenalties(2, 3, 1)
+    p, t = b"ACGTACGTAC", b"ACGTTCGAC"
+    r = oracle.align(p.decode(), t.decode(), 2, 3, 1, 100)
+    cg = r["cigar"].encode()
+    assert lib.check_cigar_edit(t, p, len(t), len(p), cg)
+    assert not lib.check_cigar_edit(p, t, len(p), len(t), cg)            # text / pattern swapped: I and D trade places
+    assert not lib.check_cigar_edit(t, p, len(t), len(p), b"9M")
+    assert lib.check_affine_distance(t, p, len(t), len(p), r["distance"], pen, cg)
+    assert not lib.check_affine_distance(t, p, len(t), len(p), r["distance"] + 1, pen, cg)

@@ -137,3 +137,48 @@ bool wfagpu_check_result(const char *pattern, size_t plen, const char *text, siz
     }
     return v == plen && h == tlen && score == error;
 }
+
+
+/* The reference's two generic validators under their own names and argument order (text first):
+ * utils/verification.h:37-49.  Exported by the reference library and used by its `-c` path. */
+static bool walk_cigar(const char *text, const char *pattern, size_t tlen, size_t plen, const char *cigar,
+                       const affine_penalties_t *pen, unsigned long *score_out)
+{
+    size_t v = 0, h = 0;
+    unsigned long score = 0;
+    const char *c = cigar;
+    if (!c || !text || !pattern) return false;
+    while (*c) {
+        unsigned long rep = 0;
+        if (*c < '0' || *c > '9') return false;
+        while (*c >= '0' && *c <= '9') rep = rep * 10 + (unsigned long)(*c++ - '0');
+        const char op = *c++;
+        if (op == 'M' || op == 'X') {
+            if (v + rep > plen || h + rep > tlen) return false;
+            for (unsigned long i = 0; i < rep; ++i)
+                if ((pattern[v + i] == text[h + i]) != (op == 'M')) return false;
+            v += rep; h += rep;
+            if (op == 'X' && pen) score += rep * (unsigned long)pen->x;
+        } else if (op == 'I') { h += rep; if (pen) score += (unsigned long)pen->o + rep * (unsigned long)pen->e; }
+        else if (op == 'D') { v += rep; if (pen) score += (unsigned long)pen->o + rep * (unsigned long)pen->e; }
+        else return false;
+        if (v > plen || h > tlen) return false;
+    }
+    if (score_out) *score_out = score;
+    return v == plen && h == tlen;
+}
+
+bool check_cigar_edit(const char *text, const char *pattern, const int tlen, const int plen, const char *curr_cigar)
+{
+    if (tlen < 0 || plen < 0) return false;
+    return walk_cigar(text, pattern, (size_t)tlen, (size_t)plen, curr_cigar, NULL, NULL);
+}
+
+bool check_affine_distance(const char *text, const char *pattern, const int tlen, const int plen, const int distance,
+                           const affine_penalties_t penalties, const char *cigar)
+{
+    unsigned long score = 0;
+    if (tlen < 0 || plen < 0 || distance < 0) return false;
+    if (!walk_cigar(text, pattern, (size_t)tlen, (size_t)plen, cigar, &penalties, &score)) return false;
+    return score == (unsigned long)distance;
+}

@@ -90,6 +90,7 @@ EXPORTS = [
     "wfagpu_synth_add_pairs", "wfagpu_device_wait", "wfagpu_host_register", "wfagpu_host_unregister",
     "wfagpu_pairs_from_metadata", "wfagpu_reset_results", "wfagpu_read_seq_file", "wfagpu_read_fasta_files",
     "wfagpu_check_result", "wfagpu_last_launch_ok", "wfagpu_plan_chunks",
+    "check_cigar_edit", "check_affine_distance", "wfagpu_cigar_append", "wfagpu_device_download_text",
 ]
 
 _lib = None
