@@ -23,3 +23,13 @@ def test_extreme_shapes():
     pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "extreme_check.py")], capture_output=True, text=True,
                         timeout=900)
     assert pr.returncode == 0, pr.stdout[-2000:] + pr.stderr[-2000:]
+
+
+def test_randomised_sweep_vs_reference_gpu_binary():
+    # needs oracle/_ref/gpu/wfa.affine.gpu (built here from /root/reference, travels with the snapshot)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gpu", "wfa.affine.gpu")):
+        pytest.skip("reference GPU binary not built")
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_vs_reference_gpu.py"), "20", "5"],
+                        capture_output=True, text=True, timeout=900)
+    assert pr.returncode == 0, pr.stdout[-2000:] + pr.stderr[-2000:]
+    assert "mismatches=0" in pr.stdout
