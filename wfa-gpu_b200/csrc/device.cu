@@ -4,9 +4,11 @@
  * Replaces the launch glue of the reference (lib/sequence_alignment.cu:31-470,
  * lib/sequence_packing.cu:96-116 and the device half of lib/align.cu:42-481):
  * buffers are grow-only and cached per device, nothing is memset per batch, the
- * decision arenas are sized by the step table, over-budget pairs are
- * re-dispatched on the GPU with a doubled wavefront budget and pairs with
- * non-ACGT bytes run through the byte-compare kernel.  There is no CPU path.
+ * snapshot / decision arenas are sized by the step table, rings and launch shape
+ * are provisioned from the scores of the previous batch, pairs that outgrow the
+ * provision or the budget are re-dispatched on the GPU with a budget picked from
+ * their score bounds, and pairs with an 'N' run through the byte-compare kernels.
+ * There is no CPU path.
  */
 #include <algorithm>
 #include <chrono>
