@@ -17,14 +17,15 @@ rb = wfagpu.ResidentBatch(a)
 rb.upload()
 plan = rb.plan()
 rb.align(plan); rb.wait()
-ms = []
+ms, wf = [], []
 for _ in range(steps):
     rb.align(plan)
     mp, ma = rb.wait()
     ms.append(ma)
+    wf.append(rb.stats()["ms_wavefront"])
 out, ops, used = rb.download()
 st = rb.stats()
 best = min(ms)
 print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("WFAGPU_")}, "pairs": n, "len": L, "err": err,
-                  "cigar": cigar, "align_ms": [round(m, 2) for m in ms], "pairs_per_s": round(n / (best / 1e3), 1),
+                  "cigar": cigar, "align_ms": [round(m, 2) for m in ms], "wavefront_ms": round(min(wf), 2), "pairs_per_s": round(n / (best / 1e3), 1),
                   "redispatched": st["redispatched"], "cells": st["cells"]}))

@@ -113,6 +113,9 @@ struct LaunchCfg {
     int A, E1, G;
     bool global_ring;     /* large tier: rings in global memory, int32 offsets */
     bool ckpt;            /* checkpointed traceback (ring snapshots) instead of decision bytes */
+    bool quad;            /* wfa_quad_kernel: four diagonals per thread, packed int16 SIMD */
+    bool quad_pairs;      /* ... and two scores per barrier interval: rings one row deeper */
+    int ring_m, ring_g;   /* rows of the M ring / of the I and D rings */
 };
 
 struct Slot {
@@ -178,7 +181,7 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
-    bool no_ckpt = false, no_bound = false, force_bound = false;
+    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false;
     int force_period = 0;
     int arena_mb = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
@@ -241,6 +244,8 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->force_warp = env_int("WFAGPU_WARP_KERNEL", -1);
     d->no_ckpt = env_int("WFAGPU_NO_CKPT", 0) != 0;
     d->no_bound = env_int("WFAGPU_NO_BOUND", 0) != 0;
+    d->no_quad = env_int("WFAGPU_NO_QUAD", 0) != 0;
+    d->no_quad_pairs = env_int("WFAGPU_NO_QUAD_PAIRS", 0) != 0;
     d->force_bound = env_int("WFAGPU_FORCE_BOUND", 0) != 0;
     d->arena_mb = env_int("WFAGPU_ARENA_MB", 0);
     d->force_period = env_int("WFAGPU_CK_PERIOD", 0);
@@ -359,12 +364,15 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
     n_want = std::max(1, n_want);
     /* ring row geometry.  Checkpointed traceback copies rows in 16-byte units: diagonal 0 sits on
      * an 8-element boundary and a row has 8 spare cells on both sides. */
-    bool ck = false;
+    bool ck = false;       /* aligned row geometry: snapshots (16-byte units) and the quad kernel (LDS.64) need it */
     auto ctr = [&](int ncap) { return ck ? ((ncap + 2 * G + 8 + 7) & ~7) : ncap + 2 * G + 1; };
     auto rs = [&](int ncap) { return ck ? 2 * ctr(ncap) : 2 * (ncap + 2 * G + 1) + 2; };
 
     c->global_ring = false;
     c->ckpt = false;
+    c->quad = false;
+    c->quad_pairs = false;
+    c->ring_m = A; c->ring_g = E1;
     bool large = d->force_large || max_len >= (1u << 15);
     if (!large) {
         /* rings that do not fit one CTA's shared memory even single-buffered go to the large tier */
@@ -410,8 +418,15 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
     }
     if (!warp) {
         c->groups_per_cta = 1;
-        ck = bt && !d->no_ckpt;
-        c->ckpt = ck;
+        c->ckpt = bt && !d->no_ckpt;
+        /* packed pairs on shared-memory rings run four diagonals per thread (with backtrace: snapshots only) */
+        c->quad = !ascii && !d->no_quad && (!bt || c->ckpt);
+        /* two scores per barrier: score d + 1 must not read the extended M of score d (x >= 2, o + e >= 2) and takes
+         * its extend sources from registers (e == 1); costs one more row per ring */
+        c->quad_pairs = c->quad && !d->no_quad_pairs && x >= 2 && o + e >= 2 && e == 1;
+        ck = c->ckpt || c->quad;
+        const int RA = A + (c->quad_pairs ? 1 : 0), RE = E1 + (c->quad_pairs ? 1 : 0);
+        c->ring_m = RA; c->ring_g = RE;
         int best_k = 0, stages = 1, n_cap = n_want;
         size_t smem = 0;
         /* CTA size follows the average width of the pruned wavefront (~ n_want): a quarter of it, 64..192
@@ -427,25 +442,26 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
             const size_t budget = std::min(smem_max, smem_sm / k - 1024);
             for (int st = 2; st >= 1; --st) {
                 if (d->force_stages && st != d->force_stages) continue;
-                if (exact_smem_bytes(A, E1, rs(n_min), seq_words, 1, st, true) > budget) continue;
+                if (exact_smem_bytes(RA, RE, rs(n_min), seq_words, 1, st, true) > budget) continue;
                 int lo = n_min, hi = n_want;             /* widest rings that still fit k CTAs */
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) / 2;
-                    if (exact_smem_bytes(A, E1, rs(mid), seq_words, 1, st, true) <= budget) lo = mid; else hi = mid - 1;
+                    if (exact_smem_bytes(RA, RE, rs(mid), seq_words, 1, st, true) <= budget) lo = mid; else hi = mid - 1;
                 }
                 best_k = k; stages = st; n_cap = lo;
-                smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, st, true);
+                smem = exact_smem_bytes(RA, RE, rs(n_cap), seq_words, 1, st, true);
                 break;
             }
         }
         if (!best_k) {
             /* does not fit even alone: hold as many diagonals as one CTA can */
             stages = 1;
-            const size_t fixed = exact_smem_bytes(A, E1, 0, seq_words, 1, stages, true);
-            if (fixed + (size_t)rows * rs(1) * 2 > smem_max) return -2;   /* the sequences alone do not fit */
-            n_cap = (int)((smem_max - fixed - 64) / ((size_t)rows * 4)) - 2 * G - (ck ? 16 : 2);
+            const size_t fixed = exact_smem_bytes(RA, RE, 0, seq_words, 1, stages, true);
+            const int rows_q = RA + 2 * RE;
+            if (fixed + (size_t)rows_q * rs(1) * 2 > smem_max) return -2;   /* the sequences alone do not fit */
+            n_cap = (int)((smem_max - fixed - 64) / ((size_t)rows_q * 4)) - 2 * G - (ck ? 16 : 2);
             if (n_cap < 1) return -2;
-            smem = exact_smem_bytes(A, E1, rs(n_cap), seq_words, 1, stages, true);
+            smem = exact_smem_bytes(RA, RE, rs(n_cap), seq_words, 1, stages, true);
             best_k = 1;
         }
         c->stages = stages;
@@ -457,13 +473,21 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
         /* (measured on B200: 3 x 384, 5 x 192 -- the per-score overhead is paid per warp) */
         int t = best_k == 1 ? 1024 : (best_k == 2 ? 512 : (best_k == 3 ? 384 : ((960 / best_k) / 32) * 32));
         const int width = 2 * n_cap + 1;
-        while (t > 64 && t * 2 > width) t -= 32;
+        if (c->quad) {
+            /* a thread covers four diagonals per trip: one to two trips over the average window (~ n_cap);
+             * the kernel needs ~80 registers: never so many threads that the registers cost a resident CTA */
+            t = std::min(std::min(t, 512), std::max(64, ((n_cap / 6) + 31) & ~31));
+            while (t > 64 && !d->force_threads && quad_max_ctas_per_sm(t, smem, bt) < best_k) t -= 32;
+        } else {
+            while (t > 64 && t * 2 > width) t -= 32;
+        }
         t = std::max(64, t);
         if (d->force_threads) t = d->force_threads;
         c->group_threads = t;
     }
     const int threads = warp ? 32 * c->groups_per_cta : c->group_threads;
-    int occ = exact_max_ctas_per_sm(c->group_threads, c->groups_per_cta, c->smem, ascii, bt, c->ckpt);
+    int occ = c->quad ? quad_max_ctas_per_sm(c->group_threads, c->smem, bt)
+                      : exact_max_ctas_per_sm(c->group_threads, c->groups_per_cta, c->smem, ascii, bt, c->ckpt);
     if (occ < 1) {
         fprintf(stderr, "[wfagpu] kernel configuration does not fit (threads=%d smem=%zu)\n", threads, c->smem);
         return -1;
@@ -783,6 +807,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.seq_words = c.seq_words;
     kp.with_bt = plan.with_cigar;
     kp.stages = c.stages;
+    kp.quad_pairs = c.quad_pairs ? 1 : 0;
+    kp.ring_m = c.ring_m; kp.ring_g = c.ring_g;
     kp.band = plan.band;
     kp.win = win;
     kp.band_lo = s.band_lo.p;
@@ -807,7 +833,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     if (env_int("WFAGPU_VERBOSE", 0))
         fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d band=%d tier=%s period=%d arena=%.1f MB\n",
                 n_items, max_steps, c.n_cap, d_end, c.group_threads, c.groups_per_cta, c.ctas, c.stages, c.smem,
-                (int)ascii, plan.band > 0 ? win : 0, c.global_ring ? "global-int32" : (c.ckpt ? "smem-int16+ckpt" : "smem-int16"), period, arenas * arena_units * 16.0 / 1e6);
+                (int)ascii, plan.band > 0 ? win : 0, c.global_ring ? "global-int32" : (c.quad ? (c.quad_pairs ? (c.ckpt ? "smem-int16x4x2+ckpt" : "smem-int16x4x2") : (c.ckpt ? "smem-int16x4+ckpt" : "smem-int16x4")) : (c.ckpt ? "smem-int16+ckpt" : "smem-int16")), period, arenas * arena_units * 16.0 / 1e6);
     int tb_ctas = 0;
     constexpr int kTbWarps = 8;
     if (c.ckpt) {
@@ -840,6 +866,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         const bool time_it = first_pass && items_per_launch >= n_items && s.ev[6] && s.ev[7];
         if (time_it) CK(cudaEventRecord(s.ev[6], s.stream));
         cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
+                      : c.quad ? launch_quad(kp, c.group_threads, (int)std::min<size_t>(c.ctas, cnt), c.smem, s.stream)
                                : launch_exact(kp, c.group_threads, c.groups_per_cta, (int)std::min<size_t>(c.ctas, cnt), c.smem, ascii, s.stream);
         if (e != cudaSuccess) {
             fprintf(stderr, "[wfagpu] alignment kernel launch failed: %s\n", cudaGetErrorString(e));

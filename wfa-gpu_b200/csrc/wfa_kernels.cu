@@ -808,6 +808,511 @@ __global__ void __launch_bounds__(WARP ? 256 : 1024, WARP ? 4 : 1) wfa_exact_ker
 }
 
 /* ======================================================================== */
+/*    CTA-per-pair wavefront kernel, four diagonals per thread (s16x2)      */
+/* ======================================================================== */
+/*
+ * Same recurrence, windows, ring layout, schedule records and snapshots as
+ * wfa_exact_kernel<false, false, BT, RingS16, CKPT> (so the traceback kernel and the
+ * parity argument are unchanged), but
+ *  (1) a thread owns FOUR adjacent diagonals k .. k+3 (k a multiple of 4) per trip:
+ *      the source rows arrive as LDS.64 + LDS.32/U16 (the k-1 / k+4 neighbours) instead of
+ *      20 x LDS.S16, the results leave as 3 x STS.64; I, D and the max of M run on packed
+ *      int16 pairs (VIMNMX.S16x2, VIADD.16x2, VIMNMX3.S16x2 -- the DPX integer SIMD of
+ *      sm_90+), the k-1 / k+1 shifts are PRMTs;
+ *  (2) the extend keeps one cell per lane-slot but its common case (the run ends within the
+ *      9 bases every packed window is good for, and the cell is more than 8 bases away from
+ *      both sequence ends) is branch-free: predicated LDS x 2, XOR, FLO, predicated add --
+ *      no clamping; everything else calls the out-of-line general extend;
+ *  (3) TWO scores per barrier when the penalties allow it (x >= 2, o + e >= 2, e == 1):
+ *      score d + 1 reads M of d - 1 and d - 3 and the I / D cells of score d, never the extended
+ *      M of score d, so a thread computes its quad for d and d + 1 back to back; the two I / D cells
+ *      of score d it needs from its neighbours (k - 1 for I, k + 4 for D) it recomputes from the old
+ *      rows (two packed ops).  Halves the barriers and the per-score control work.
+ * Cells of a quad outside a score's window [lo, hi] are written as NULL, so the rings hold exactly
+ * what the one-diagonal-per-thread kernel leaves in them wherever a later score or a snapshot reads.
+ */
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t a, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+__device__ __noinline__ int extend_packed_general(uint32_t Pa, uint32_t Ta, int plen, int tlen, int k, int off)
+{
+    return extend_packed(Pa, Ta, plen, tlen, k, off, kOffNull);
+}
+
+/* The common case of an extend, branch-free so that the four cells of a quad overlap: returns the
+ * XOR of the two 16-base windows at (m - k, m), or 0 when the cell is NULL or within 8 bases of the end of a
+ * sequence (limp = max(min(plen + k, tlen) - 8, 0)).  A result >= 0x4000 means the run ends within the 9
+ * bases every window is good for and nothing has to be clamped: m += clz >> 1. */
+__device__ __forceinline__ uint32_t extend_probe(uint32_t Pa, uint32_t Ta, int k, int m, int limp)
+{
+    const uint32_t uv = (uint32_t)(m - k), uh = (uint32_t)m;
+    uint32_t ap, at, wp = 0, wt = 0;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(ap) : "r"(uv >> 3), "r"(Pa));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(at) : "r"(uh >> 3), "r"(Ta));
+    /* predicated loads (no branch): a NULL or near-the-end cell loads nothing and yields 0 */
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.lt.u32 p, %4, %5;\n"
+                 "@p ld.shared.u32 %0, [%2];\n"
+                 "@p ld.shared.u32 %1, [%3];\n"
+                 "}\n" : "+r"(wp), "+r"(wt) : "r"(ap), "r"(at), "r"((uint32_t)m), "r"((uint32_t)limp));
+    return (wp << ((uv & 7u) * 2u)) ^ (wt << ((uh & 7u) * 2u));
+}
+
+/* m += clz(f) >> 1 when f >= 0x4000 (a run of at most 8 bases), predicated */
+__device__ __forceinline__ int add_run(int m, uint32_t f)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 t;\n"
+        "setp.ge.u32 p, %1, 0x4000;\n"
+        "bfind.u32 t, %1;\n"
+        "shr.u32 t, t, 1;\n"
+        "sub.s32 t, 15, t;\n"
+        "@p add.s32 %0, %0, t;\n"
+        "}\n" : "+r"(m) : "r"(f));
+    return m;
+}
+
+constexpr uint32_t kNull2 = 0x83008300u;          /* two int16 NULLs (-32000) */
+constexpr uint32_t kOnes2 = 0x00010001u;
+
+/* mask of the cells (k, k+1) inside [lo, hi]; packed value with the cells outside replaced by NULL */
+__device__ __forceinline__ uint32_t in2(int k, int lo, int hi)
+{
+    return ((k >= lo && k <= hi) ? 0xffffu : 0u) | ((k + 1 >= lo && k + 1 <= hi) ? 0xffff0000u : 0u);
+}
+__device__ __forceinline__ uint32_t sel2(uint32_t v, uint32_t mask) { return (v & mask) | (kNull2 & ~mask); }
+
+/* extend the four M cells (M01 | M23) of the quad that starts at diagonal kq */
+__device__ __forceinline__ void extend_quad(uint32_t Pa, uint32_t Ta, int plen, int tlen, int kq, int tl8,
+                                            uint32_t &M01, uint32_t &M23)
+{
+    const int c8 = kq + plen - 8;
+    int m0 = (int)(short)(M01 & 0xffffu), m1 = (int)M01 >> 16;
+    int m2 = (int)(short)(M23 & 0xffffu), m3 = (int)M23 >> 16;
+    const uint32_t f0 = extend_probe(Pa, Ta, kq, m0, __viaddmin_s32_relu(c8, 0, tl8));
+    const uint32_t f1 = extend_probe(Pa, Ta, kq + 1, m1, __viaddmin_s32_relu(c8, 1, tl8));
+    const uint32_t f2 = extend_probe(Pa, Ta, kq + 2, m2, __viaddmin_s32_relu(c8, 2, tl8));
+    const uint32_t f3 = extend_probe(Pa, Ta, kq + 3, m3, __viaddmin_s32_relu(c8, 3, tl8));
+    /* z < 0x4000: a valid cell whose probe did not settle it -- a long run (the cells on the alignment
+     * path) or a cell next to the end of a sequence: rare, out of line */
+    const uint32_t z0 = f0 | ((uint32_t)m0 & 0x80000000u), z1 = f1 | ((uint32_t)m1 & 0x80000000u);
+    const uint32_t z2 = f2 | ((uint32_t)m2 & 0x80000000u), z3 = f3 | ((uint32_t)m3 & 0x80000000u);
+    m0 = add_run(m0, f0);
+    m1 = add_run(m1, f1);
+    m2 = add_run(m2, f2);
+    m3 = add_run(m3, f3);
+    if (min(min(z0, z1), min(z2, z3)) < 0x4000u) {
+        if (z0 < 0x4000u) m0 = extend_packed_general(Pa, Ta, plen, tlen, kq, m0);
+        if (z1 < 0x4000u) m1 = extend_packed_general(Pa, Ta, plen, tlen, kq + 1, m1);
+        if (z2 < 0x4000u) m2 = extend_packed_general(Pa, Ta, plen, tlen, kq + 2, m2);
+        if (z3 < 0x4000u) m3 = extend_packed_general(Pa, Ta, plen, tlen, kq + 3, m3);
+    }
+    M01 = __byte_perm((uint32_t)m0, (uint32_t)m1, 0x5410);
+    M23 = __byte_perm((uint32_t)m2, (uint32_t)m3, 0x5410);
+}
+
+template <bool BT, bool COUNT>
+__global__ void __launch_bounds__(512, 1) wfa_quad_kernel(const __grid_constant__ KernelParams p)
+{
+    constexpr bool CKPT = BT;                     /* with backtrace: ring snapshots (wfa_traceback_kernel follows) */
+    constexpr int NULLV = kOffNull;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x, gsz = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, last_warp = (gsz >> 5) - 1;
+
+    /* ---- shared memory: [rings][sequence stages][ctl][schedule records] (layout of wfa_exact_kernel) ---- */
+    /* ring depths: one row more than the recurrence needs when two scores share a barrier interval (the
+     * second score would otherwise overwrite rows d - A and d - e - 1 = sources of the first) */
+    const int RM = p.ring_m, RG = p.ring_g;
+    const int rows = RM + 2 * RG;
+    const uint32_t row_bytes = (uint32_t)p.row_stride * 2u;
+    const uint32_t ring_bytes = ((uint32_t)rows * row_bytes + 15u) & ~15u;
+    const uint32_t seq_bytes = (uint32_t)p.seq_words * 4u;
+    const uint32_t seq_total = 2u * (uint32_t)p.stages * seq_bytes;
+    unsigned char *gbase = smem_raw;
+    const uint32_t ring_sa = smem_u32(gbase);
+    const uint32_t seq_sa = ring_sa + ring_bytes;
+    GroupCtl *ctl = reinterpret_cast<GroupCtl *>(gbase + ring_bytes + seq_total);
+    const uint32_t sched_sa = ring_sa + ring_bytes + seq_total + (uint32_t)sizeof(GroupCtl);
+
+    const int x = p.x, e = p.e, A = p.A, GW = p.G;
+    const int oe = p.o + p.e;
+    const bool pairable = p.quad_pairs != 0;      /* two scores per barrier (host: x >= 2, o + e >= 2, e == 1, deeper rings) */
+    const uint32_t M0 = ring_sa + 2u * (uint32_t)p.center;            /* row 0 of M, diagonal 0 (16-byte aligned) */
+    const uint32_t I0 = M0 + (uint32_t)RM * row_bytes;
+    const uint32_t D0 = I0 + (uint32_t)RG * row_bytes;
+    const uint32_t Mend = M0 + (uint32_t)RM * row_bytes, Iend = I0 + (uint32_t)RG * row_bytes, Dend = D0 + (uint32_t)RG * row_bytes;
+
+    uint4 *arena = p.arena;
+
+    auto issue_load = [&](int stage, uint32_t idx) {
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const uint32_t pw = ((((pr.plen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        const uint32_t tw = ((((pr.tlen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        unsigned char *dp = gbase + ring_bytes + (size_t)(2 * stage) * seq_bytes;
+        unsigned char *dt = dp + seq_bytes;
+        fence_proxy_async();
+        mbar_expect_tx(&ctl->bar[stage], (pw + tw) * 4u);
+        tma_load_1d(dp, p.packed + pr.p_word, pw * 4u, &ctl->bar[stage]);
+        tma_load_1d(dt, p.packed + pr.t_word, tw * 4u, &ctl->bar[stage]);
+    };
+    auto pop = [&](int slot) -> uint32_t {
+        const uint32_t pos = atomicAdd(p.queue, 1u);
+        ctl->pos[slot] = pos;
+        return pos < p.n_items ? p.order[pos] : kInvalidIdx;
+    };
+
+    if (tid == 0) {
+        mbar_init(&ctl->bar[0], 1);
+        mbar_init(&ctl->bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t first = pop(0);
+        ctl->idx[0] = first;
+        if (first != kInvalidIdx) issue_load(0, first);
+    }
+    __syncthreads();
+
+    int stage = 0;
+    uint32_t phase_bits = 0;
+
+    while (true) {
+        const uint32_t idx = ctl->idx[stage];
+        if (idx == kInvalidIdx) break;
+        if (CKPT) arena = p.arena + (size_t)ctl->pos[stage] * p.arena_units;
+        if (tid == 0 && p.stages == 2) {
+            const uint32_t nxt = pop(stage ^ 1);
+            ctl->idx[stage ^ 1] = nxt;
+            if (nxt != kInvalidIdx) issue_load(stage ^ 1, nxt);
+        }
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const int plen = (int)pr.plen, tlen = (int)pr.tlen;
+        const int kt = tlen - plen;
+        const uint32_t Pa = seq_sa + (uint32_t)(2 * stage) * seq_bytes;
+        const uint32_t Ta = Pa + seq_bytes;
+        const bool skip = (pr.flags & WFAGPU_PAIR_HAS_N) != 0;       /* left to the byte-compare launch */
+
+        /* ring prologue: NULL over [-2G - 4, 2G + 4] on every row */
+        {
+            const int span = 4 * GW + 9;
+            const int total = rows * span;
+            for (int i = tid; i < total; i += gsz) {
+                const int r = i / span;
+                const int k = i - r * span - 2 * GW - 4;
+                sts_16(M0 + (uint32_t)r * row_bytes + (uint32_t)(2 * k), NULLV);
+            }
+        }
+        mbar_wait(&ctl->bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        __syncthreads();
+
+        int dist = 0;
+        bool finished = false;
+
+        if (!skip) {
+            const int Dmax = p.bound ? min(p.d_end - 1, p.bound[idx]) : p.d_end - 1;
+            /* schedule records of scores dbase .. dbase + kSchedBlock - 1 (warp 0, one score per lane) */
+            auto fill_sched = [&](int dbase, int buf) {
+                const int d = dbase + tid;
+                StepRec r;
+                r.lo = 0; r.hi = -1; r.flags = kRecStop; r.n = 0; r.ck_j = 0;
+                r.aMc = r.aMx = r.aMo = r.aIc = r.aIe = r.aDc = r.aDe = 0;
+                if (d <= Dmax) {
+                    const wfagpu_step_t st = p.steps[d];
+                    int lo, hi;
+                    const bool live = prune_window((int)st.n, kt, (Dmax - d) / e, p.n_cap, lo, hi);
+                    const bool stop = live && (lo < -p.n_cap || hi > p.n_cap);
+                    const bool work = live && st.kind != WFAGPU_STEP_NULL;
+                    r.lo = lo; r.hi = hi; r.n = (int)st.n;
+                    r.flags = (uint32_t)st.kind | (live ? kRecLive : 0u) | (stop ? kRecStop : 0u) |
+                              ((work && kt >= lo && kt <= hi) ? kRecTarget : 0u) |
+                              ((CKPT && d % p.ck_period == 0) ? kRecSnap : 0u);
+                    r.ck_j = CKPT ? (uint32_t)(d / p.ck_period) : 0u;
+                    const int dm = d % RM, de1 = d % RG;
+                    int sx = dm - x % RM; if (sx < 0) sx += RM;
+                    int so = dm - oe % RM; if (so < 0) so += RM;
+                    int se = de1 - e % RG; if (se < 0) se += RG;
+                    r.aMc = M0 + (uint32_t)dm * row_bytes;
+                    r.aMx = M0 + (uint32_t)sx * row_bytes;
+                    r.aMo = M0 + (uint32_t)so * row_bytes;
+                    r.aIc = I0 + (uint32_t)de1 * row_bytes;
+                    r.aIe = I0 + (uint32_t)se * row_bytes;
+                    r.aDc = D0 + (uint32_t)de1 * row_bytes;
+                    r.aDe = D0 + (uint32_t)se * row_bytes;
+                }
+                const uint32_t a = sched_sa + (uint32_t)(buf * kSchedBlock + tid) * (uint32_t)sizeof(StepRec);
+                sts_v4(a, make_uint4((uint32_t)r.lo, (uint32_t)r.hi, r.flags, (uint32_t)r.n));
+                sts_v4(a + 16u, make_uint4(r.aMc, r.aMx, r.aMo, r.aIc));
+                sts_v4(a + 32u, make_uint4(r.aIe, r.aDc, r.aDe, r.ck_j));
+            };
+            auto rec_addr = [&](int d) -> uint32_t {
+                return sched_sa + (uint32_t)((((d - 1) / kSchedBlock) & 1) * kSchedBlock + ((d - 1) & (kSchedBlock - 1))) * (uint32_t)sizeof(StepRec);
+            };
+            if (tid == 0) sts_16(M0, extend_packed(Pa, Ta, plen, tlen, 0, 0, NULLV));
+            if (tid < kSchedBlock) fill_sched(1, 0);
+            __syncthreads();
+            if (kt == 0 && lds_s16(M0) == tlen) {
+                finished = true;
+            } else {
+                const int tl8 = tlen - 8;
+                unsigned long long n_cells = 0;
+                /* snapshot of the ring rows later scores can still read (layout: wfa_exact_kernel) */
+                auto checkpoint = [&](uint32_t aMc, uint32_t aIc, uint32_t aDc, int ck_j, int n, int lo, int hi) {
+                    if constexpr (CKPT) {
+                        const int pitch = (((n + 7) & ~7) + ((n + 8) & ~7)) >> 3;
+                        const int k0 = max((lo - 1) & ~7, -((n + 7) & ~7));
+                        const int units = ((min((hi + 1) | 7, ((n + 8) & ~7) - 1) - k0) + 1) >> 3;
+                        uint4 *dst = arena + p.ck_off[ck_j] + ((k0 + ((n + 7) & ~7)) >> 3);
+                        uint32_t row = aMc;
+                        for (int a = 0; a < A - 1; ++a) {
+                            for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
+                            dst += pitch;
+                            row = (row == M0) ? Mend - row_bytes : row - row_bytes;
+                        }
+                        row = aIc;
+                        for (int a = 0; a < e; ++a) {
+                            for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
+                            dst += pitch;
+                            row = (row == I0) ? Iend - row_bytes : row - row_bytes;
+                        }
+                        row = aDc;
+                        for (int a = 0; a < e; ++a) {
+                            for (int q = tid; q < units; q += gsz) __stcs(dst + q, lds_v4(row + (uint32_t)(2 * k0) + 16u * (uint32_t)q));
+                            dst += pitch;
+                            row = (row == D0) ? Dend - row_bytes : row - row_bytes;
+                        }
+                    }
+                };
+                /* guard cells: NULL on both sides of the quads [kq0, kend] of a row triple (one warp writes them) */
+                auto guards = [&](uint32_t aMc, uint32_t aIc, uint32_t aDc, int kq0, int kend) {
+                    for (int g = lane; g < 2 * GW; g += 32) {
+                        const int k = (g < GW) ? (kq0 - 1 - g) : (kend + 1 + (g - GW));
+                        sts_16(aMc + (uint32_t)(2 * k), NULLV);
+                        sts_16(aIc + (uint32_t)(2 * k), NULLV);
+                        sts_16(aDc + (uint32_t)(2 * k), NULLV);
+                    }
+                };
+                int last_blk = -1;
+                int d = 1;
+                while (d <= Dmax) {
+                    const int blk = (d - 1) / kSchedBlock;
+                    if (blk != last_blk) {
+                        /* first trip in this block of records: warp 0 derives the next block (the other buffer
+                         * held block blk - 1, which nobody reads any more: a barrier has passed since) */
+                        last_blk = blk;
+                        if (tid < kSchedBlock) fill_sched((blk + 1) * kSchedBlock + 1, (blk + 1) & 1);
+                    }
+                    const uint32_t ra = rec_addr(d);
+                    const uint4 r0 = lds_v4(ra), r1 = lds_v4(ra + 16u), r2 = lds_v4(ra + 32u);
+                    if (r0.z & kRecStop) break;
+                    const int lo = (int)r0.x, hi = (int)r0.y;
+                    const int kind = (int)(r0.z & 3u);
+                    const bool live = (r0.z & kRecLive) != 0;
+                    const uint32_t aMc = r1.x, aMx = r1.y, aMo = r1.z, aIc = r1.w, aIe = r2.x, aDc = r2.y, aDe = r2.z;
+                    if (COUNT && live && kind != WFAGPU_STEP_NULL) n_cells += (unsigned)(hi - lo + 1);
+
+                    if (kind == WFAGPU_STEP_MDI && live) {
+                        /* ---- can the next score ride along? ---- */
+                        uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0, s2 = s0;
+                        bool two = false;
+                        if (pairable && d < Dmax) {
+                            const uint32_t rb = rec_addr(d + 1);
+                            s0 = lds_v4(rb);
+                            two = (s0.z & (3u | kRecLive | kRecStop)) == (WFAGPU_STEP_MDI | kRecLive);
+                            if (two) { s1 = lds_v4(rb + 16u); s2 = lds_v4(rb + 32u); }
+                        }
+                        if (!two) {
+                            const int kq0 = lo & ~3, kend = hi | 3;
+                            if (warp == last_warp) guards(aMc, aIc, aDc, kq0, kend);
+                            for (int kq = kq0 + 4 * tid; kq <= hi; kq += 4 * gsz) {
+                                const uint32_t o2 = (uint32_t)(2 * kq);
+                                const uint2 mo = lds_v2(aMo + o2);
+                                const uint32_t ml = lds_u16(aMo + o2 - 2u), mr = lds_u16(aMo + o2 + 8u);
+                                const uint2 ie = lds_v2(aIe + o2);
+                                const uint32_t il = lds_u16(aIe + o2 - 2u);
+                                const uint2 de = lds_v2(aDe + o2);
+                                const uint32_t dr = lds_u16(aDe + o2 + 8u);
+                                const uint2 mx = lds_v2(aMx + o2);
+                                /* (k-1 | k), (k+1 | k+2) and (k+3 | k+4) views of the open-gap source row */
+                                const uint32_t moL01 = __byte_perm(ml, mo.x, 0x5410);
+                                const uint32_t moMid = __byte_perm(mo.x, mo.y, 0x5432);
+                                const uint32_t moR23 = __byte_perm(mo.y, mr, 0x5432);
+                                uint32_t I01 = __vadd2(__vmaxs2(moL01, __byte_perm(il, ie.x, 0x5410)), kOnes2);
+                                uint32_t I23 = __vadd2(__vmaxs2(moMid, __byte_perm(ie.x, ie.y, 0x5432)), kOnes2);
+                                uint32_t D01 = __vmaxs2(moMid, __byte_perm(de.x, de.y, 0x5432));
+                                uint32_t D23 = __vmaxs2(moR23, __byte_perm(de.y, dr, 0x5432));
+                                uint32_t M01 = __vimax3_s16x2(__vadd2(mx.x, kOnes2), D01, I01);
+                                uint32_t M23 = __vimax3_s16x2(__vadd2(mx.y, kOnes2), D23, I23);
+                                if (kq < lo || kq + 3 > hi) {
+                                    /* quad straddles the window: cells outside [lo, hi] read as NULL */
+                                    const uint32_t k01 = in2(kq, lo, hi), k23 = in2(kq + 2, lo, hi);
+                                    I01 = sel2(I01, k01); D01 = sel2(D01, k01); M01 = sel2(M01, k01);
+                                    I23 = sel2(I23, k23); D23 = sel2(D23, k23); M23 = sel2(M23, k23);
+                                }
+                                sts_v2(aIc + o2, I01, I23);
+                                sts_v2(aDc + o2, D01, D23);
+                                extend_quad(Pa, Ta, plen, tlen, kq, tl8, M01, M23);
+                                sts_v2(aMc + o2, M01, M23);
+                            }
+                            __syncthreads();
+                            if ((r0.z & kRecTarget) != 0 && lds_s16(aMc + (uint32_t)(2 * kt)) == tlen) { finished = true; dist = d; break; }
+                            if ((r0.z & kRecSnap) != 0) checkpoint(aMc, aIc, aDc, (int)r2.w, (int)r0.w, lo, hi);
+                            d += 1;
+                            continue;
+                        }
+                        /* ---- scores d and d + 1 in one barrier interval (e == 1: the extend sources of d + 1
+                         *      are the I / D cells of d, kept in registers; its M sources are older rows) ---- */
+                        const int lo2 = (int)s0.x, hi2 = (int)s0.y;
+                        const uint32_t bMc = s1.x, bMx = s1.y, bMo = s1.z, bIc = s1.w, bDc = s2.y;
+                        if (COUNT) n_cells += (unsigned)(hi2 - lo2 + 1);
+                        const int kq0 = min(lo, lo2) & ~3, kend = max(hi, hi2) | 3;
+                        if (warp == last_warp) { guards(aMc, aIc, aDc, kq0, kend); guards(bMc, bIc, bDc, kq0, kend); }
+                        for (int kq = kq0 + 4 * tid; kq <= kend; kq += 4 * gsz) {
+                            const uint32_t o2 = (uint32_t)(2 * kq);
+                            /* score d: rows d-4 (open), d-1 (extend), d-2 (mismatch); the words at k-2 and k+4 carry
+                             * the neighbours' cells and what their I / D cells of score d are made of */
+                            const uint2 mo = lds_v2(aMo + o2);
+                            const uint32_t mlw = lds_u32(aMo + o2 - 4u), mrw = lds_u32(aMo + o2 + 8u);   /* (k-2|k-1), (k+4|k+5) */
+                            const uint2 ie = lds_v2(aIe + o2);
+                            const uint32_t ilw = lds_u32(aIe + o2 - 4u);
+                            const uint2 de = lds_v2(aDe + o2);
+                            const uint32_t drw = lds_u32(aDe + o2 + 8u);
+                            const uint2 mx = lds_v2(aMx + o2);
+                            const uint32_t moL01 = __byte_perm(mlw, mo.x, 0x5432);                        /* (k-1 | k)   */
+                            const uint32_t moMid = __byte_perm(mo.x, mo.y, 0x5432);                       /* (k+1 | k+2) */
+                            const uint32_t moR23 = __byte_perm(mo.y, mrw, 0x5432);                        /* (k+3 | k+4) */
+                            uint32_t I01 = __vadd2(__vmaxs2(moL01, __byte_perm(ilw, ie.x, 0x5432)), kOnes2);
+                            uint32_t I23 = __vadd2(__vmaxs2(moMid, __byte_perm(ie.x, ie.y, 0x5432)), kOnes2);
+                            uint32_t D01 = __vmaxs2(moMid, __byte_perm(de.x, de.y, 0x5432));
+                            uint32_t D23 = __vmaxs2(moR23, __byte_perm(de.y, drw, 0x5432));
+                            /* neighbours' cells of score d: I of (k-1 | k) and D of (k+3 | k+4) */
+                            uint32_t IL = __vadd2(__vmaxs2(mlw, ilw), kOnes2);
+                            uint32_t DR = __vmaxs2(mrw, drw);
+                            uint32_t M01 = __vimax3_s16x2(__vadd2(mx.x, kOnes2), D01, I01);
+                            uint32_t M23 = __vimax3_s16x2(__vadd2(mx.y, kOnes2), D23, I23);
+                            if (kq - 1 < lo || kq + 4 > hi) {
+                                const uint32_t k01 = in2(kq, lo, hi), k23 = in2(kq + 2, lo, hi);
+                                I01 = sel2(I01, k01); D01 = sel2(D01, k01); M01 = sel2(M01, k01);
+                                I23 = sel2(I23, k23); D23 = sel2(D23, k23); M23 = sel2(M23, k23);
+                                IL = sel2(IL, in2(kq - 1, lo, hi));
+                                DR = sel2(DR, in2(kq + 3, lo, hi));
+                            }
+                            sts_v2(aIc + o2, I01, I23);
+                            sts_v2(aDc + o2, D01, D23);
+                            extend_quad(Pa, Ta, plen, tlen, kq, tl8, M01, M23);
+                            sts_v2(aMc + o2, M01, M23);
+                            /* score d + 1: rows d-3 (open), d-1 (mismatch); extend sources from the registers */
+                            const uint2 no = lds_v2(bMo + o2);
+                            const uint32_t nl = lds_u16(bMo + o2 - 2u), nr = lds_u16(bMo + o2 + 8u);
+                            const uint2 nx = lds_v2(bMx + o2);
+                            const uint32_t noMid = __byte_perm(no.x, no.y, 0x5432);
+                            uint32_t J01 = __vadd2(__vmaxs2(__byte_perm(nl, no.x, 0x5410), IL), kOnes2);
+                            uint32_t J23 = __vadd2(__vmaxs2(noMid, __byte_perm(I01, I23, 0x5432)), kOnes2);
+                            uint32_t E01 = __vmaxs2(noMid, __byte_perm(D01, D23, 0x5432));
+                            uint32_t E23 = __vmaxs2(__byte_perm(no.y, nr, 0x5432), DR);
+                            uint32_t N01 = __vimax3_s16x2(__vadd2(nx.x, kOnes2), E01, J01);
+                            uint32_t N23 = __vimax3_s16x2(__vadd2(nx.y, kOnes2), E23, J23);
+                            if (kq < lo2 || kq + 3 > hi2) {
+                                const uint32_t k01 = in2(kq, lo2, hi2), k23 = in2(kq + 2, lo2, hi2);
+                                J01 = sel2(J01, k01); E01 = sel2(E01, k01); N01 = sel2(N01, k01);
+                                J23 = sel2(J23, k23); E23 = sel2(E23, k23); N23 = sel2(N23, k23);
+                            }
+                            sts_v2(bIc + o2, J01, J23);
+                            sts_v2(bDc + o2, E01, E23);
+                            extend_quad(Pa, Ta, plen, tlen, kq, tl8, N01, N23);
+                            sts_v2(bMc + o2, N01, N23);
+                        }
+                        __syncthreads();
+                        /* same order as score by score: an alignment that ends at d + 1 is traced back from the snapshot of d */
+                        if ((r0.z & kRecTarget) != 0 && lds_s16(aMc + (uint32_t)(2 * kt)) == tlen) { finished = true; dist = d; break; }
+                        if ((r0.z & kRecSnap) != 0) checkpoint(aMc, aIc, aDc, (int)r2.w, (int)r0.w, lo, hi);
+                        if ((s0.z & kRecTarget) != 0 && lds_s16(bMc + (uint32_t)(2 * kt)) == tlen) { finished = true; dist = d + 1; break; }
+                        if ((s0.z & kRecSnap) != 0) checkpoint(bMc, bIc, bDc, (int)s2.w, (int)s0.w, lo2, hi2);
+                        /* the next interval recycles the rows of scores d - 3 (M) and d (I, D), which the snapshot of
+                         * score d is still copying in slower warps */
+                        if ((r0.z & kRecSnap) != 0) __syncthreads();
+                        d += 2;
+                        continue;
+                    }
+                    if (kind == WFAGPU_STEP_NULL || !live) {
+                        for (int k = lo - GW - 4 + tid; k <= hi + GW + 4; k += gsz) {
+                            sts_16(aMc + (uint32_t)(2 * k), NULLV);
+                            sts_16(aIc + (uint32_t)(2 * k), NULLV);
+                            sts_16(aDc + (uint32_t)(2 * k), NULLV);
+                        }
+                        __syncthreads();
+                        if ((r0.z & kRecSnap) != 0) checkpoint(aMc, aIc, aDc, (int)r2.w, (int)r0.w, lo, hi);
+                        d += 1;
+                        continue;
+                    }
+                    /* mismatch-only step (the first scores, before any gap wavefront exists) */
+                    for (int k = lo - GW - 4 + tid; k <= hi + GW + 4; k += gsz) {
+                        sts_16(aIc + (uint32_t)(2 * k), NULLV);
+                        sts_16(aDc + (uint32_t)(2 * k), NULLV);
+                        int m = NULLV;
+                        if (k >= lo && k <= hi) {
+                            m = lds_s16(aMx + (uint32_t)(2 * k)) + 1;
+                            if (m >= 0) m = extend_packed(Pa, Ta, plen, tlen, k, m, NULLV);
+                        }
+                        sts_16(aMc + (uint32_t)(2 * k), m);
+                    }
+                    __syncthreads();
+                    if ((r0.z & kRecTarget) != 0 && lds_s16(aMc + (uint32_t)(2 * kt)) == tlen) { finished = true; dist = d; break; }
+                    if ((r0.z & kRecSnap) != 0) checkpoint(aMc, aIc, aDc, (int)r2.w, (int)r0.w, lo, hi);
+                    d += 1;
+                }
+                if (COUNT && tid == 0) atomicAdd(p.cells, n_cells);
+            }
+        }
+
+        if (tid == 0) {
+            wfagpu_pair_out_t r;
+            r.distance = finished ? dist : 0;
+            r.ops_off = 0;
+            r.n_ops = 0;
+            if (skip) {
+                r.status = WFAGPU_ST_NEEDS_ASCII;
+                p.ascii_list[atomicAdd(p.ascii_count, 1u)] = idx;
+            } else if (finished) {
+                r.status = WFAGPU_ST_FINISHED;
+            } else {
+                r.status = WFAGPU_ST_OVERBUDGET;
+                p.retry_list[atomicAdd(p.retry_count, 1u)] = idx;
+            }
+            p.out[idx] = r;
+        }
+        __syncthreads();
+        if (p.stages == 2) {
+            stage ^= 1;
+        } else {
+            if (tid == 0) {
+                const uint32_t nxt = pop(0);
+                ctl->idx[0] = nxt;
+                if (nxt != kInvalidIdx) issue_load(0, nxt);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+
+/* ======================================================================== */
 /*              score upper bound (warp per pair, 32 diagonals)             */
 /* ======================================================================== */
 /*
@@ -1751,6 +2256,39 @@ int traceback_max_ctas_per_sm(int A, int period, int warps, bool ascii)
                    : (bt ? FN<true, false, true>(__VA_ARGS__) : FN<true, false, false>(__VA_ARGS__)))    \
           : (ascii ? (bt ? FN<false, true, true>(__VA_ARGS__) : FN<false, true, false>(__VA_ARGS__))     \
                    : (bt ? FN<false, false, true>(__VA_ARGS__) : FN<false, false, false>(__VA_ARGS__))))
+
+template <bool BT, bool COUNT>
+static cudaError_t launch_quad_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
+{
+    auto kfn = wfa_quad_kernel<BT, COUNT>;
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kfn<<<ctas, threads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_quad(const KernelParams &p, int threads, int ctas, size_t smem_bytes, cudaStream_t s)
+{
+    if (p.with_bt && !p.ck_off) return cudaErrorInvalidValue;       /* with backtrace: ring snapshots only */
+    if (p.cells)        /* instrumented build of the same kernel: counts the cells of every window */
+        return p.with_bt ? launch_quad_one<true, true>(p, threads, ctas, smem_bytes, s) : launch_quad_one<false, true>(p, threads, ctas, smem_bytes, s);
+    return p.with_bt ? launch_quad_one<true, false>(p, threads, ctas, smem_bytes, s) : launch_quad_one<false, false>(p, threads, ctas, smem_bytes, s);
+}
+
+int quad_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt)
+{
+    int n = 0;
+    if (bt) {
+        auto kfn = wfa_quad_kernel<true, false>;
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
+    } else {
+        auto kfn = wfa_quad_kernel<false, false>;
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
+    }
+    return n;
+}
 
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
                          size_t smem_bytes, bool ascii, cudaStream_t s)

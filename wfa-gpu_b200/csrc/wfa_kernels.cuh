@@ -62,6 +62,8 @@ struct KernelParams {
     int32_t *band_lo;             /* banded kernel: per group, lo of every score (traceback) */
     uint32_t band_lo_words;
     int stages;                   /* 1 or 2 sequence buffers per group (2 = prefetch next pair) */
+    int quad_pairs;               /* quad kernel: two scores per barrier (needs ring_m = A + 1, ring_g = E1 + 1) */
+    int ring_m, ring_g;           /* quad kernel: rows of the M ring and of the I / D rings */
     /* decision arena: one region per worker group */
     int32_t *gring;               /* large tier: per-group rings in global memory, else null */
     uint64_t gring_elems;         /* int32 elements per group                                */
@@ -111,6 +113,10 @@ void launch_cigar_text(const CigarParams &p, cudaStream_t s);
 /* group_threads == 32 -> warp-per-pair variant; otherwise CTA-per-pair */
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,
                          size_t smem_bytes, bool ascii_extend, cudaStream_t s);
+/* CTA per pair, four diagonals per thread (packed sequences, shared-memory rings whose diagonal 0 is 16-byte
+ * aligned; with backtrace it writes ring snapshots: p.ck_off must be set) */
+cudaError_t launch_quad(const KernelParams &p, int threads, int ctas, size_t smem_bytes, cudaStream_t s);
+int quad_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt);
 /* per-pair score upper bounds for the pruning (warp per pair) */
 cudaError_t launch_bound(const KernelParams &p, int ctas, int warps, cudaStream_t s);
 size_t bound_smem_bytes(int A, int E1, int warps);
