@@ -21,7 +21,8 @@ extern "C" {
 #endif
 
 /* Longest sequence wfagpu_add_sequences accepts (the reference: MAX_SEQ_LEN - 1 = 32767). */
-#define WFAGPU_MAX_SEQ_LEN ((size_t)1 << 22)
+/* The large tier stages both packed sequences of a pair in one CTA's shared memory (227 KB): 2 x len / 2 bytes. */
+#define WFAGPU_MAX_SEQ_LEN ((size_t)220000)
 
 /* ---------------------------------------------------------- step table --- */
 /* Per-score control record.  It depends on the penalties and the step budget
@@ -71,6 +72,8 @@ typedef struct {
 #define WFAGPU_ST_FINISHED   1u
 #define WFAGPU_ST_OVERBUDGET 2u /* needs a larger wavefront budget (re-dispatch) */
 #define WFAGPU_ST_NEEDS_ASCII 4u /* flagged by the packer: byte-compare kernel    */
+#define WFAGPU_ST_FAILED 8u      /* the GPU cannot finish this pair (> 60000 wavefront steps or wavefronts wider than
+                                  * one CTA holds); set by wfagpu_device_download, the other pairs keep their results */
 
 /* Where a pair's CIGAR text sits in the text pool returned by wfagpu_device_download_text. */
 typedef struct {
@@ -100,12 +103,15 @@ typedef struct {
     uint64_t cells;           /* wavefront cells computed (0 unless profiling)  */
     uint64_t h2d_bytes, d2h_bytes;
     float ms_wavefront;       /* the first pass's wavefront kernel alone (0 if it ran in several sub-launches) */
-    float reserved0;
+    uint32_t failed_pairs;    /* pairs reported as WFAGPU_ST_FAILED                                            */
 } wfagpu_batch_stats_t;
 
-/* Opens (or returns the cached) context of CUDA device `dev`. NULL on failure
- * (message on stderr); never falls back to the CPU. */
+/* Leases a context of CUDA device `dev`: an idle one from the pool (with its grown buffers) or a new one; the
+ * caller owns it until wfagpu_device_release.  Two leases never share streams, slots or staging buffers, so
+ * threads (or two workers on one GPU) do not interfere.  NULL on failure (message on stderr); never falls
+ * back to the CPU.  wfagpu_device_close_all frees every context (none may be in use). */
 wfagpu_device_t *wfagpu_device_open(int dev);
+void wfagpu_device_release(wfagpu_device_t *d);
 void wfagpu_device_close_all(void);
 
 /*
@@ -140,6 +146,13 @@ void wfagpu_device_last_stats(wfagpu_device_t *d, int slot, wfagpu_batch_stats_t
  * H2D copies run as asynchronous DMA. */
 int wfagpu_host_register(void *ptr, size_t bytes);
 int wfagpu_host_unregister(void *ptr);
+/* 1 if `ptr` is page-locked memory. */
+int wfagpu_host_is_pinned(const void *ptr);
+/* Page-locked staging area of a slot for callers with a pageable sequence buffer (see driver.c). */
+char *wfagpu_device_staging(wfagpu_device_t *d, int slot, size_t bytes);
+/* Page-locked zeroed host memory (NULL without a usable CUDA device: callers fall back to calloc). */
+void *wfagpu_host_alloc(size_t bytes);
+void wfagpu_host_free(void *p);
 int wfagpu_device_sm_count(wfagpu_device_t *d);
 
 /* Builds the device-side descriptors of pairs [from, from+n) of a host buffer
@@ -183,11 +196,24 @@ typedef struct {
     uint64_t redispatched;
     uint64_t ascii_pairs;
     uint64_t h2d_bytes, d2h_bytes;
-    int devices;
+    int devices;          /* workers (one leased context each) */
+    int staged;           /* 1: the caller's buffer was pageable, chunks went through page-locked staging */
+    uint64_t failed_pairs; /* pairs the GPU could not finish (results[i].error == UINT_MAX)               */
+    uint64_t checked, incorrect; /* check_correctness: pairs validated / found wrong                      */
 } wfagpu_run_stats_t;
+/* Statistics / outcome of the calling thread's last launch_alignments* call (thread-local). */
 void wfagpu_last_run_stats(wfagpu_run_stats_t *st);
-/* false when the last launch_alignments* call failed on the GPU (nothing is computed on the CPU) */
+/* false when that call failed on the GPU or left pairs unaligned (nothing is computed on the CPU) */
 bool wfagpu_last_launch_ok(void);
+/* Device list syntax of wfagpu_set_devices / WFAGPU_DEVICES (pure function; -1 on a bad list). */
+int wfagpu_parse_devices(const char *spec, int visible, int *devs, int max_devs);
+/* Independent re-computation of the scores of the batch resident in `slot` (check_correctness): score only,
+ * one-diagonal-per-thread kernels, launch bound only -- no per-pair bounds, packed-SIMD kernel, snapshots or
+ * provisioning hints.  scores[i] = -1 for a pair it could not finish. */
+int wfagpu_device_rescore(wfagpu_device_t *d, int slot, size_t n, const wfagpu_plan_t *plan, int32_t *scores);
+
+/* Makes room for `bytes` more sequence bytes and `pairs` more pairs in one step (readers, generators). */
+bool wfagpu_reserve(wfagpu_aligner_t *aligner, size_t bytes, size_t pairs);
 
 /* Clears errors and CIGAR text of a previous wfagpu_align (the reference, like
  * this library, appends to results[i].cigar) so an aligner can be re-aligned. */
@@ -205,12 +231,21 @@ long wfagpu_read_fasta_files(wfagpu_aligner_t *aligner, const char *query_path, 
 bool wfagpu_check_result(const char *pattern, size_t plen, const char *text, size_t tlen,
                          affine_penalties_t pen, unsigned int error, const char *cigar);
 
-/* The reference library's generic validators, same names and argument order (text first;
- * utils/verification.h:37-49): the CIGAR is a global alignment of (pattern, text) / its gap-affine
+/* The reference library's generic validators, same names, argument order (text first) and input format
+ * (utils/verification.h:37-58): the op string may be UNROLLED ("MMXMMI", what the reference's recover_cigar
+ * returns and lib/align.cu:284-293 passes) or the run-length text of results[i].cigar.buffer ("2M1X2M1I").
+ * check_cigar_edit: the ops are a global alignment of (pattern, text); check_affine_distance: their gap-affine
  * cost equals `distance`. */
 bool check_cigar_edit(const char *text, const char *pattern, const int tlen, const int plen, const char *curr_cigar);
 bool check_affine_distance(const char *text, const char *pattern, const int tlen, const int plen, const int distance,
                            const affine_penalties_t penalties, const char *cigar);
+/* recover_cigar (utils/verification.h:52-58): unrolled op string from a reference-format backtrace chain
+ * (calloc'ed, caller frees). */
+char *recover_cigar(const char *text, const char *pattern, const size_t tlen, const size_t plen,
+                    wfa_backtrace_t final_backtrace, wfa_backtrace_t *offloaded_backtraces_array,
+                    alignment_result_t result);
+/* Unrolled op string of run-length CIGAR text (malloc'ed, caller frees; NULL on malformed text). */
+char *wfagpu_unroll_cigar(const char *rle);
 
 /* Deterministic synthetic pairs (text uniform over ACGT, pattern =
  * text with ceil(L*err) edits, each uniformly mismatch / 1-base deletion /

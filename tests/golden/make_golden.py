@@ -10,6 +10,10 @@ Run in the build container (needs /root/reference); the outputs are committed:
   api_10k.json.gz      tests/data/sequences_10K.h: 100 pairs x 10 kbp + goldens x2o3e1 / x3o5e2
   api_1000.json.gz     tests/data/sequences_1000.h: first 300 of 1000 pairs x 1 kbp + goldens
                        x2o3e1 / x5o3e2        [asserted by tests/test_api.c:59-219]
+  test_hifi.{query,target}.fasta.gz + test_hifi.json
+                       tests/data/test_hifi.*.fasta (50 HiFi pairs, the reference's FASTA fixture,
+                       tests/test-fasta.sh:11-22) verbatim, with the record lengths and the scores of the
+                       UNMODIFIED reference CPU WFA (oracle/_ref/libref_cpu.so) for penalties (2,3,1) and (5,2,5)
 """
 import gzip, json, os, re
 
@@ -59,8 +63,41 @@ def header(path, seq_name, golden_names, limit=None):
     return obj
 
 
+def hifi():
+    import shutil, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT), "..", "oracle"))
+    from oracle import RefCPU
+    recs = {}
+    for side in ("query", "target"):
+        src = f"{REF}/tests/data/test_hifi.{side}.fasta"
+        with open(src, "rb") as f, gzip.open(os.path.join(OUT, f"test_hifi.{side}.fasta.gz"), "wb", compresslevel=9) as g:
+            shutil.copyfileobj(f, g)
+        seqs, cur = [], None
+        for line in open(src):
+            line = line.strip()
+            if not line:
+                continue
+            if line.lstrip().startswith(">"):
+                if cur is not None:
+                    seqs.append("".join(cur))
+                cur = []
+            else:
+                cur.append(line)
+        seqs.append("".join(cur))
+        recs[side] = seqs
+    assert len(recs["query"]) == len(recs["target"]) == 50
+    r = RefCPU()
+    obj = {"lengths": [[len(q), len(t)] for q, t in zip(recs["query"], recs["target"])], "scores": {}}
+    for pen in ((2, 3, 1), (5, 2, 5)):
+        errs, _ = r.align_batch(recs["query"], recs["target"], *pen, cigar=False)
+        obj["scores"]["%d,%d,%d" % pen] = list(errs)
+    with open(os.path.join(OUT, "test_hifi.json"), "w") as f:
+        json.dump(obj, f)
+
+
 if __name__ == "__main__":
     utest()
+    hifi()
     dump("api_10k.json.gz", header(f"{REF}/tests/data/sequences_10K.h", "sequences_10K_n100",
                                    ["results_10K_n100_x2o3e1", "results_10K_n100_x3o5e2"]))
     dump("api_1000.json.gz", header(f"{REF}/tests/data/sequences_1000.h", "sequences_1000_n1000",

@@ -219,3 +219,122 @@ def test_reference_validator_names(lib, oracle):
     assert not lib.check_cigar_edit(t, p, len(t), len(p), b"9M")
     assert lib.check_affine_distance(t, p, len(t), len(p), r["distance"], pen, cg)
     assert not lib.check_affine_distance(t, p, len(t), len(p), r["distance"] + 1, pen, cg)
+
+
+def test_validators_take_the_reference_unrolled_format(lib, oracle):
+    # the reference calls check_cigar_edit / check_affine_distance with the UNROLLED op string of recover_cigar
+    # (lib/align.cu:284-293, utils/verification.c:27-146); the run-length text of results[i].cigar is accepted too
+    import ctypes as C
+    pen = wfagpu.AffinePenalties(2, 3, 1)
+    p, t = "GATTACAGATTACAGGATCCA", "GATTACGATTTACAGGTCCA"
+    r = oracle.align(p, t, 2, 3, 1, 100)
+    rle = r["cigar"].encode()
+    ptr = lib.wfagpu_unroll_cigar(rle)
+    unrolled = C.string_at(ptr)
+    assert re.fullmatch(rb"[MXID]+", unrolled) and len(unrolled) >= max(len(p), len(t))
+    pb, tb = p.encode(), t.encode()
+    for cg in (rle, unrolled):
+        assert lib.check_cigar_edit(tb, pb, len(tb), len(pb), cg)
+        assert lib.check_affine_distance(tb, pb, len(tb), len(pb), r["distance"], pen, cg)
+        assert not lib.check_affine_distance(tb, pb, len(tb), len(pb), r["distance"] + 1, pen, cg)
+    assert not lib.check_cigar_edit(tb, pb, len(tb), len(pb), unrolled[:-1])
+    assert not lib.check_cigar_edit(tb, pb, len(tb), len(pb), unrolled.replace(b"X", b"M", 1))
+    assert lib.wfagpu_unroll_cigar(b"3M1") is None and lib.wfagpu_unroll_cigar(b"3M0X") is None
+
+
+def test_recover_cigar_decodes_reference_format_chains(lib, oracle):
+    # recover_cigar (utils/verification.h:52-58) on backtrace chains in the reference's own layout (produced by the
+    # restatement of its kernels): the unrolled string must be the unrolled form of the reference decoder's text
+    import ctypes as C
+
+    class Bt(C.Structure):
+        _fields_ = [("backtrace", C.c_uint32), ("prev", C.c_uint32)]
+
+    class Res(C.Structure):
+        _fields_ = [("finished", C.c_bool), ("distance", C.c_int), ("bt", Bt), ("num_bt_blocks", C.c_int)]
+
+    lib.recover_cigar.restype = C.c_void_p
+    lib.recover_cigar.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, Bt, C.POINTER(Bt), Res]
+    a = wfagpu.Aligner()
+    a.add_synthetic(0xB2007700, 6, 400, 0.08, 0.12)
+    a.add_synthetic(0xB2007701, 6, 60, 0.0, 0.3)
+    for i in range(a.num_pairs):
+        p, t = a.pair(i)
+        fin, dist, final_word, words = oracle.align_chain(p, t, 2, 3, 1, 400)
+        assert fin
+        arr = (Bt * max(1, len(words)))(*[Bt(w, 0) for w in words])
+        res = Res(True, dist, Bt(final_word, 0), len(words))
+        got = C.string_at(lib.recover_cigar(t.encode(), p.encode(), len(t), len(p), Bt(final_word, 0), arr, res))
+        want = C.string_at(lib.wfagpu_unroll_cigar(oracle.align(p, t, 2, 3, 1, 400)["cigar"].encode()))
+        assert got == want, i
+
+
+def test_device_list_syntax(lib):
+    import ctypes as C
+    devs = (C.c_int * 16)()
+    f = lib.wfagpu_parse_devices
+    assert f(None, 4, devs, 16) == 1 and devs[0] == 0
+    assert f(b"all", 4, devs, 16) == 4 and list(devs[:4]) == [0, 1, 2, 3]
+    assert f(b"n:2", 4, devs, 16) == 2 and list(devs[:2]) == [0, 1]
+    assert f(b"n:8", 4, devs, 16) == 4
+    assert f(b"0,2,3", 4, devs, 16) == 3 and list(devs[:3]) == [0, 2, 3]
+    assert f(b"0,0", 1, devs, 16) == 2 and list(devs[:2]) == [0, 0]        # two workers, own contexts, one GPU
+    assert f(b"0,7", 4, devs, 16) == -1                                      # not a visible device
+    assert f(b"0;1", 4, devs, 16) == -1 and f(b"x", 4, devs, 16) == -1
+
+
+def test_chunk_plan(lib):
+    import ctypes as C
+    chunk, n = C.c_size_t(), C.c_size_t()
+    f = lambda *a: (lib.wfagpu_plan_chunks(*a, C.byref(chunk), C.byref(n)), (chunk.value, n.value))[1]
+    assert f(100, 100, 1, 10**6) == (100, 1)                                 # small call: one chunk
+    assert f(8192, 8192, 1, 8192 * 20000) == (2048, 4)                       # default batch size: four chunks per worker
+    assert f(8192, 1000, 1, 8192 * 20000) == (1000, 9)                       # the caller's batch size is an upper bound
+    assert f(8192, 8192, 2, 8192 * 20000) == (1024, 8)
+    assert f(3000, 3000, 2, 3000 * 300) == (750, 4)                          # several GPUs: at least two chunks each
+    assert f(4, 4, 8, 4000)[0] >= 1
+    c, k = f(10**6, 10**6, 1, 10**6 * 20000)                                 # a chunk's ASCII stays below 3 GiB
+    assert c * 20000 <= 3 * 2**30 and c * k >= 10**6
+
+
+def test_metadata_must_be_word_aligned(lib):
+    import ctypes as C
+    a = wfagpu.Aligner()
+    a.add_sequences("ACGTACGTAC", "ACGTTCGAC")
+    a.add_sequences("ACGT", "ACGA")
+    pairs = (wfagpu.DevPair * 2)()
+    base, nbytes = C.c_size_t(), C.c_size_t()
+    assert lib.wfagpu_pairs_from_metadata(a.s.sequences_metadata, 0, 2, a.s.sequences_buffer_len, pairs, C.byref(base), C.byref(nbytes)) == 0
+    a.s.sequences_metadata[1].pattern_offset += 1                            # the pack kernel selects 32-bit words
+    assert lib.wfagpu_pairs_from_metadata(a.s.sequences_metadata, 0, 2, a.s.sequences_buffer_len, pairs, C.byref(base), C.byref(nbytes)) != 0
+    a.s.sequences_metadata[1].pattern_offset -= 1
+
+
+def test_sequences_longer_than_the_large_tier_are_rejected(lib):
+    a = wfagpu.Aligner()
+    assert not a.add_sequences("A" * 220000, "ACGT")
+    assert a.add_sequences("A" * 1000, "ACGT")
+
+
+def hifi_fixture(tmp_path):
+    """The reference's FASTA fixture (tests/data/test_hifi.*.fasta), unpacked from tests/golden."""
+    import gzip, json, shutil
+    out = []
+    for side in ("query", "target"):
+        dst = tmp_path / f"test_hifi.{side}.fasta"
+        with gzip.open(os.path.join(ROOT, "tests", "golden", f"test_hifi.{side}.fasta.gz"), "rb") as f, open(dst, "wb") as g:
+            shutil.copyfileobj(f, g)
+        out.append(str(dst))
+    return out[0], out[1], json.load(open(os.path.join(ROOT, "tests", "golden", "test_hifi.json")))
+
+
+def test_hifi_fasta_fixture_reads_like_the_reference(lib, tmp_path):
+    # the reference's FASTA fixture (tests/test-fasta.sh:11-22: 50 pairs, `correct=50`), committed as a golden copy
+    q, t, gold = hifi_fixture(tmp_path)
+    a = wfagpu.Aligner()
+    assert a.read_fasta_files(q, t) == 50
+    lens = [[a.s.sequences_metadata[i].pattern_len, a.s.sequences_metadata[i].text_len] for i in range(50)]
+    assert lens == gold["lengths"]
+    for i in (0, 17, 49):
+        p, tt = a.pair(i)
+        assert set(p) <= set("ACGTN") and set(tt) <= set("ACGTN")

@@ -137,6 +137,7 @@ struct Slot {
     DevBuf<char> slots, text;
     DevBuf<wfagpu_cigar_ref_t> refs;
     DevBuf<unsigned long long> heads;
+    PinBuf<char> h_ascii;              /* staging for callers whose sequence buffer is pageable */
     PinBuf<char> h_text;
     PinBuf<wfagpu_cigar_ref_t> h_refs;
     PinBuf<unsigned long long> h_heads;
@@ -191,10 +192,49 @@ struct wfagpu_device {
     bool use_hint = true;
     bool force_large = false;
     bool device_text = true;   /* WFAGPU_HOST_CIGAR=1 leaves the text to the host */
+    bool leased = false;       /* handed out by wfagpu_device_open and not released yet */
+    bool independent = false;  /* wfagpu_device_rescore in progress: do not learn hints from it */
+    int max_steps_cap = 60000; /* most wavefront steps a pair may take (WFAGPU_MAX_STEPS_CAP lowers it: tests) */
 };
 
+/* Contexts are leased: wfagpu_device_open hands out an idle context of that GPU (or makes a new one), so two
+ * host threads -- or two workers of one call on the same GPU ("0,0") -- never share streams, slots or staging
+ * buffers; wfagpu_device_release returns it to the pool with its grown buffers.  Only the provisioning hint
+ * (largest / mean score of the last batch per penalty set) is shared per GPU, under g_mu. */
+struct DevShared {
+    int dev = -1;
+    int hint_dist = 0;
+    double hint_mean = 0;
+    int hint_key[3] = {-1, -1, -1};
+};
 static std::mutex g_mu;
 static std::vector<wfagpu_device *> g_devices;
+static std::vector<DevShared> g_shared;
+
+static DevShared &shared_of(int dev)          /* g_mu held */
+{
+    for (auto &h : g_shared) if (h.dev == dev) return h;
+    DevShared h;
+    h.dev = dev;
+    g_shared.push_back(h);
+    return g_shared.back();
+}
+static void pull_hint(wfagpu_device *d)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    const DevShared &h = shared_of(d->dev);
+    d->hint_dist = d->use_hint ? h.hint_dist : 0;
+    d->hint_mean = h.hint_mean;
+    d->hint_key[0] = h.hint_key[0]; d->hint_key[1] = h.hint_key[1]; d->hint_key[2] = h.hint_key[2];
+}
+static void push_hint(wfagpu_device *d)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevShared &h = shared_of(d->dev);
+    h.hint_dist = d->hint_dist;
+    h.hint_mean = d->hint_mean;
+    h.hint_key[0] = d->hint_key[0]; h.hint_key[1] = d->hint_key[1]; h.hint_key[2] = d->hint_key[2];
+}
 
 static int env_int(const char *name, int dflt)
 {
@@ -206,8 +246,9 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto *d : g_devices)
-        if (d->dev == dev) {
+        if (d->dev == dev && !d->leased) {
             cudaSetDevice(dev);
+            d->leased = true;
             return d;
         }
     int count = 0;
@@ -255,8 +296,17 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
     d->force_large = env_int("WFAGPU_FORCE_LARGE", 0) != 0;
     d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;
+    d->max_steps_cap = std::min(60000, std::max(16, env_int("WFAGPU_MAX_STEPS_CAP", 60000)));
+    d->leased = true;
     g_devices.push_back(d);
     return d;
+}
+
+extern "C" void wfagpu_device_release(wfagpu_device_t *d)
+{
+    if (!d) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    d->leased = false;
 }
 
 extern "C" void wfagpu_device_close_all(void)
@@ -270,7 +320,7 @@ extern "C" void wfagpu_device_close_all(void)
             s.retry[0].release(); s.retry[1].release(); s.ascii_list.release(); s.out.release();
             s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release(); s.bound.release(); s.ck_off.release(); s.h_ck32.release(); s.h_bound.release(); s.h_retry.release();
             s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release(); s.slots.release(); s.text.release(); s.refs.release(); s.heads.release();
-            s.h_text.release(); s.h_refs.release(); s.h_heads.release();
+            s.h_text.release(); s.h_refs.release(); s.h_heads.release(); s.h_ascii.release();
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
             s.h_counters.release(); s.h_cells.release(); s.h_steps.release();
             for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -279,6 +329,7 @@ extern "C" void wfagpu_device_close_all(void)
         delete d;
     }
     g_devices.clear();
+    g_shared.clear();
 }
 
 extern "C" int wfagpu_device_sm_count(wfagpu_device_t *d) { return d ? d->prop.multiProcessorCount : 0; }
@@ -517,6 +568,7 @@ static void learn_hint(wfagpu_device *d, Slot &s, size_t n)
     d->hint_dist = d->use_hint ? dmax : 0;
     d->hint_mean = cnt ? sum / (double)cnt : 0;
     d->hint_key[0] = s.plan.x; d->hint_key[1] = s.plan.o; d->hint_key[2] = s.plan.e;
+    push_hint(d);
 }
 
 /* Ring-snapshot layout of the checkpointed traceback for period P: snapshot j (score j * P) holds
@@ -611,6 +663,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
                        bool *capped_out, bool have_bounds = false)
 {
     HostTrace tr;
+    if (first_pass) pull_hint(d);            /* what the last batch on this GPU needed (any context) */
     if (ensure_step_table(s, plan, max_steps)) return -1;
     const wfagpu_step_t *tab = s.h_steps.p;
     const int d_full = s.tab_d_end;
@@ -932,6 +985,11 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
 {
     (void)resident;
     if (!d || slot < 0 || slot > 1 || !plan) return -1;
+    if (plan->x < 1 || plan->e < 1 || plan->o < 0) {
+        /* x = 0 or e = 0 make a wavefront its own source (and divide by zero in the pruning quotient) */
+        fprintf(stderr, "[wfagpu] penalties must satisfy x >= 1, e >= 1, o >= 0 (got %d,%d,%d)\n", plan->x, plan->o, plan->e);
+        return -3;
+    }
     CK(cudaSetDevice(d->dev));
     Slot &s = d->slots[slot];
     if (n != s.n) return -1;
@@ -987,7 +1045,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
      * -> the number of wavefront steps that is enough for all of them, 0 if one has no bound. */
     auto bound_budget = [&](int cur, uint32_t pending, long long *need) -> int {
         *need = 0;
-        constexpr int kMaxSteps = 60000;
+        const int kMaxSteps = d->max_steps_cap;
         int rc = run_bound_only(d, s, replan, kMaxSteps, s.retry[cur].p, pending);
         if (rc) return rc;
         if (s.h_bound.ensure(s.n + 1) || s.h_retry.ensure(pending + 1)) return -1;
@@ -1012,6 +1070,18 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     /* ---- re-dispatch tier: pairs that outgrew the provisioned rings or the budget get, in one go,
      * the budget their score bounds call for (and are pruned by them); without bounds (banded,
      * byte-compare pairs) first the full budget, then the budget doubles until everything finishes ---- */
+    /* pairs the GPU cannot finish (more than 60000 wavefront steps, or wavefronts wider than one CTA can hold):
+     * their indices, taken from a device retry list */
+    std::vector<uint32_t> failed;
+    auto fail_pending = [&](int buf, uint32_t count) -> int {
+        if (count == 0) return 0;
+        if (s.h_retry.ensure((size_t)count + 1)) return -1;
+        CK(cudaMemcpyAsync(s.h_retry.p, s.retry[buf].p, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        for (uint32_t i = 0; i < count; ++i)
+            if (s.h_retry.p[i] < s.n) failed.push_back(s.h_retry.p[i]);
+        return 0;
+    };
     auto redispatch = [&](bool ascii, int start_steps, bool capped) -> int {
         int cur = 0;
         long long steps = start_steps;
@@ -1028,9 +1098,10 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
                 if (rcb < 0) return rcb;
                 if (rcb == 0 && need > 0) { next = need; have_bounds = true; }
             }
-            if (next > 60000) {
-                fprintf(stderr, "[wfagpu] %u pairs need more than %lld wavefront steps; not supported yet\n", pending, steps);
-                return -4;
+            if (next > d->max_steps_cap) {
+                /* per pair, not per job: these pairs are reported as failed, everything else keeps its result */
+                fprintf(stderr, "[wfagpu] %u pairs need more than %lld wavefront steps; reported as failed\n", pending, steps);
+                return fail_pending(cur, pending);
             }
             steps = next;
             bool now_capped = false;
@@ -1039,9 +1110,9 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
             if (rc) return rc;
             if (read_counters()) return -1;
             if (now_capped && s.h_counters.p[CTR_RETRY] > 0) {
-                fprintf(stderr, "[wfagpu] %u pairs exceed the on-chip wavefront capacity; not supported yet\n",
+                fprintf(stderr, "[wfagpu] %u pairs exceed the wavefront capacity of one CTA; reported as failed\n",
                         s.h_counters.p[CTR_RETRY]);
-                return -4;
+                return fail_pending(cur ^ 1, s.h_counters.p[CTR_RETRY]);
             }
             capped = false;
             pending = s.h_counters.p[CTR_RETRY];
@@ -1075,8 +1146,14 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
     if (pair_flags) CK(cudaMemcpyAsync(s.h_pairs.p, s.pairs.p, n * sizeof(wfagpu_pair_t), cudaMemcpyDeviceToHost, s.stream));
     if (d->count_cells) CK(cudaMemcpyAsync(s.h_cells.p, s.cells.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
+    for (uint32_t idx : failed) {
+        s.h_out.p[idx].status = WFAGPU_ST_FAILED;
+        s.h_out.p[idx].distance = -1;
+        s.h_out.p[idx].n_ops = 0;
+    }
+    s.stats.failed_pairs = (uint32_t)failed.size();
     memcpy(out, s.h_out.p, n * sizeof(wfagpu_pair_out_t));
-    learn_hint(d, s, n);
+    if (!d->independent) learn_hint(d, s, n);
     if (pair_flags)
         for (size_t i = 0; i < n; ++i) pair_flags[i] = s.h_pairs.p[i].flags;
     if (ops) *ops = s.h_pool.p;
@@ -1089,6 +1166,26 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
         cudaEventElapsedTime(&s.stats.ms_align, s.ev[3], s.ev[5]);
         cudaEventElapsedTime(&s.stats.ms_total, s.ev[0], s.ev[5]);
     }
+    return 0;
+}
+
+extern "C" int wfagpu_device_rescore(wfagpu_device_t *d, int slot, size_t n, const wfagpu_plan_t *plan, int32_t *scores)
+{
+    if (!d || !plan || !scores || slot < 0 || slot > 1) return -1;
+    if (n != d->slots[slot].n) return -1;
+    /* a different code path on purpose: what it shares with the production path is the packing, the step table
+     * and the extend */
+    const bool nb = d->no_bound, nq = d->no_quad, uh = d->use_hint;
+    const int fw = d->force_warp;
+    d->no_bound = true; d->no_quad = true; d->use_hint = false; d->force_warp = 0; d->independent = true;
+    wfagpu_plan_t p2 = *plan;
+    p2.with_cigar = 0;
+    std::vector<wfagpu_pair_out_t> out(n);
+    int rc = wfagpu_device_align(d, slot, n, &p2, 1);
+    if (!rc) rc = wfagpu_device_download(d, slot, n, out.data(), nullptr, nullptr, nullptr);
+    d->no_bound = nb; d->no_quad = nq; d->use_hint = uh; d->force_warp = fw; d->independent = false;
+    if (rc) return rc;
+    for (size_t i = 0; i < n; ++i) scores[i] = (out[i].status & WFAGPU_ST_FINISHED) ? out[i].distance : -1;
     return 0;
 }
 
@@ -1111,6 +1208,40 @@ extern "C" int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, 
         learn_hint(d, s, s.n);
     }
     return 0;
+}
+
+/* 1 if `ptr` is page-locked (cudaHostAlloc / cudaHostRegister), 0 if pageable or unknown */
+extern "C" int wfagpu_host_is_pinned(const void *ptr)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return at.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
+/* Page-locked staging area of a slot (grow-only): a caller with a pageable sequence buffer copies the batch here
+ * (with its own threads) and uploads from it, so that the H2D copy is asynchronous DMA like for pinned callers.
+ * The previous upload from this slot must have been waited for (download). */
+extern "C" char *wfagpu_device_staging(wfagpu_device_t *d, int slot, size_t bytes)
+{
+    if (!d || slot < 0 || slot > 1) return nullptr;
+    if (cudaSetDevice(d->dev) != cudaSuccess) return nullptr;
+    Slot &s = d->slots[slot];
+    if (s.h_ascii.ensure(bytes + 64)) return nullptr;
+    return s.h_ascii.p;
+}
+
+/* Page-locked host memory for the aligner's own buffers (the reference's TODO, utils/sequence_reader.c:73):
+ * NULL when no CUDA device / driver is usable -- the caller then falls back to plain calloc. */
+extern "C" void *wfagpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    memset(p, 0, bytes);
+    return p;
+}
+extern "C" void wfagpu_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int wfagpu_host_register(void *ptr, size_t bytes)

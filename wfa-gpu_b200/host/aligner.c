@@ -49,12 +49,42 @@ static void owned_results_free(wfa_alignment_result_t *r)
     free(blk);
 }
 
+/* The sequence buffer is what every batch is uploaded from.  The reference callocs it and leaves "CudaMallocHost
+ * instead of calloc" as a TODO (utils/sequence_reader.c:73); here it is page-locked from the start, so an
+ * unmodified caller of wfagpu_add_sequences / wfagpu_align gets asynchronous DMA uploads without calling any
+ * extension.  A hidden 64-byte prefix remembers how the block was obtained (without a usable CUDA device it is
+ * plain calloc memory).  Buffers that do not come from here -- a caller of launch_alignments with its own
+ * malloc'ed buffer -- are staged chunk by chunk (driver.c). */
+#define SEQ_PREFIX 64
+#define SEQ_MAGIC 0x5746414750554231ull
+typedef struct { unsigned long long magic; int pinned; } seq_prefix_t;
+
+static char *seqbuf_new(size_t bytes)
+{
+    int pinned = 1;
+    char *blk = (char *)wfagpu_host_alloc(bytes + SEQ_PREFIX);
+    if (!blk) { pinned = 0; blk = (char *)calloc(bytes + SEQ_PREFIX, 1); }
+    if (!blk) return NULL;
+    seq_prefix_t *pf = (seq_prefix_t *)blk;
+    pf->magic = SEQ_MAGIC;
+    pf->pinned = pinned;
+    return blk + SEQ_PREFIX;
+}
+static void seqbuf_free(char *buf)
+{
+    if (!buf) return;
+    seq_prefix_t *pf = (seq_prefix_t *)(buf - SEQ_PREFIX);
+    if (pf->magic != SEQ_MAGIC) { free(buf); return; }      /* not ours (a caller swapped the pointer) */
+    pf->magic = 0;
+    if (pf->pinned) wfagpu_host_free(pf); else free(pf);
+}
+
 bool wfagpu_initialize_aligner(wfagpu_aligner_t *aligner)
 {
     if (!aligner) { ERR("Invalid aligner."); return false; }
     memset(aligner, 0, sizeof(*aligner));
     aligner->last_sequence_pair_idx = -1;
-    aligner->sequences_buffer = (wfagpu_seqbuf_t *)calloc(SEQ_BUF_CHUNK, 1);
+    aligner->sequences_buffer = (wfagpu_seqbuf_t *)seqbuf_new(SEQ_BUF_CHUNK);
     aligner->sequences_metadata = (sequence_pair_t *)calloc(META_CHUNK, sizeof(sequence_pair_t));
     if (!aligner->sequences_buffer || !aligner->sequences_metadata) {
         ERR("Can not initialize the aligner buffers.");
@@ -65,18 +95,39 @@ bool wfagpu_initialize_aligner(wfagpu_aligner_t *aligner)
     return true;
 }
 
+static bool reserve_pairs(wfagpu_aligner_t *a, size_t need);
 static bool reserve_bytes(wfagpu_aligner_t *a, size_t need)
 {
     if (need < a->sequences_buffer_len) return true;
     size_t nlen = a->sequences_buffer_len;
     /* geometric growth: the reference adds 1 MiB at a time, which is quadratic for GB inputs */
     while (nlen <= need) nlen += (nlen / 2 > SEQ_BUF_CHUNK ? nlen / 2 : SEQ_BUF_CHUNK);
-    char *nb = (char *)realloc(a->sequences_buffer, nlen);
+    char *nb = seqbuf_new(nlen);                             /* zeroed */
     if (!nb) return false;
-    memset(nb + a->sequences_buffer_len, 0, nlen - a->sequences_buffer_len);
+    size_t used = 0;
+    if (a->last_sequence_pair_idx >= 0) {
+        const sequence_pair_t *last = &a->sequences_metadata[a->last_sequence_pair_idx];
+        used = last->text_offset + last->text_len + 1;
+        if (used > a->sequences_buffer_len) used = a->sequences_buffer_len;
+    }
+    memcpy(nb, a->sequences_buffer, used);
+    seqbuf_free(a->sequences_buffer);
     a->sequences_buffer = nb;
     a->sequences_buffer_len = nlen;
     return true;
+}
+
+/* Extension for the readers and generators: make room for `bytes` more sequence bytes and `pairs` more pairs
+ * in one step (a page-locked buffer is expensive to grow geometrically). */
+bool wfagpu_reserve(wfagpu_aligner_t *aligner, size_t bytes, size_t pairs)
+{
+    if (!aligner || !aligner->sequences_buffer || !aligner->sequences_metadata) return false;
+    size_t used = 0;
+    if (aligner->last_sequence_pair_idx >= 0) {
+        const sequence_pair_t *last = &aligner->sequences_metadata[aligner->last_sequence_pair_idx];
+        used = WFA_ALIGN_32_BITS(last->text_offset + last->text_len + 1);
+    }
+    return reserve_bytes(aligner, used + bytes + 16) && reserve_pairs(aligner, (size_t)(aligner->last_sequence_pair_idx + 1) + pairs);
 }
 
 static bool reserve_pairs(wfagpu_aligner_t *a, size_t need)
@@ -169,7 +220,7 @@ bool wfagpu_set_batch_size(wfagpu_aligner_t *aligner, size_t batch_size)
 void wfagpu_destroy_aligner(wfagpu_aligner_t *aligner)
 {
     if (!aligner) return;
-    free(aligner->sequences_buffer);
+    seqbuf_free(aligner->sequences_buffer);
     free(aligner->sequences_metadata);
     owned_results_free(aligner->results);
     aligner->sequences_buffer = NULL;

@@ -3,62 +3,90 @@
  * (replaces the host half of lib/align.cu:42-881 and utils/wfa_cpu.c:30-164).
  *
  * The pair range is cut into chunks of at most `batch_size` pairs.  Each
- * selected GPU is driven by one host thread that owns two device slots: while
- * the GPU aligns chunk c, the thread turns the op streams of chunk c-1 into
- * CIGAR text.  Pairs are independent, so GPUs never exchange data (no NCCL):
- * results are written straight into alignment_results[i], disjoint per chunk.
- * There is no CPU alignment path: over-budget and non-ACGT pairs are finished
- * on the GPU inside wfagpu_device_download().
+ * selected GPU is driven by one host thread that leases its own device context
+ * (two slots): while the GPU aligns chunk c, the thread hands chunk c-1's
+ * results to the caller.  Pairs are independent, so GPUs never exchange data
+ * (no NCCL): results are written straight into alignment_results[i], disjoint
+ * per chunk.  There is no CPU alignment path: over-budget and non-ACGT pairs
+ * are finished on the GPU inside wfagpu_device_download().
+ *
+ * Re-entrant like the reference (lib/align.cu:63-162 allocates per call): a call
+ * owns its job, its workers and their leased contexts; the only process-wide
+ * state is the default device list (wfagpu_set_devices, mutex) and, per thread,
+ * the statistics of that thread's last call.
  */
 #include <pthread.h>
 #include <stdio.h>
 #include <string.h>
 #include <time.h>
+#include <limits.h>
 #include <omp.h>
 #include "wfagpu_b200.h"
 
 #define MAX_DEVICES 64
 
+static pthread_mutex_t g_spec_mu = PTHREAD_MUTEX_INITIALIZER;
 static char g_device_spec[256] = "";
-static wfagpu_run_stats_t g_last_stats;
-static bool g_last_ok = true;
+static __thread wfagpu_run_stats_t t_last_stats;
+static __thread bool t_last_ok = true;
 
 void wfagpu_set_devices(const char *spec)
 {
-    if (!spec) { g_device_spec[0] = 0; return; }
-    strncpy(g_device_spec, spec, sizeof(g_device_spec) - 1);
-    g_device_spec[sizeof(g_device_spec) - 1] = 0;
+    pthread_mutex_lock(&g_spec_mu);
+    if (!spec) g_device_spec[0] = 0;
+    else {
+        strncpy(g_device_spec, spec, sizeof(g_device_spec) - 1);
+        g_device_spec[sizeof(g_device_spec) - 1] = 0;
+    }
+    pthread_mutex_unlock(&g_spec_mu);
 }
 
-void wfagpu_last_run_stats(wfagpu_run_stats_t *st) { if (st) *st = g_last_stats; }
-bool wfagpu_last_launch_ok(void) { return g_last_ok; }
+void wfagpu_last_run_stats(wfagpu_run_stats_t *st) { if (st) *st = t_last_stats; }
+bool wfagpu_last_launch_ok(void) { return t_last_ok; }
 
-static int parse_devices(int *devs)
+/* Device list of a call: "all", "n:4", or ids ("0,2,5"; an id may repeat: every entry is one worker with its
+ * own context, "0,0" drives GPU 0 from two host threads).  Returns the number of workers, -1 on a bad id. */
+int wfagpu_parse_devices(const char *spec, int visible, int *devs, int max_devs)
 {
-    const char *spec = g_device_spec[0] ? g_device_spec : getenv("WFAGPU_DEVICES");
-    int visible = 0;
-    get_num_cuda_devices(&visible);
     int n = 0;
     if (!spec || !*spec) { devs[0] = 0; return 1; }
     if (!strcmp(spec, "all")) {
-        for (int i = 0; i < visible && i < MAX_DEVICES; ++i) devs[n++] = i;
-        return n ? n : 1;
+        for (int i = 0; i < visible && i < max_devs; ++i) devs[n++] = i;
+        if (!n) { devs[0] = 0; n = 1; }
+        return n;
     }
     if (!strncmp(spec, "n:", 2)) {
-        int want = atoi(spec + 2);
-        for (int i = 0; i < want && i < visible && i < MAX_DEVICES; ++i) devs[n++] = i;
+        const int want = atoi(spec + 2);
+        for (int i = 0; i < want && i < visible && i < max_devs; ++i) devs[n++] = i;
         if (!n) { devs[0] = 0; n = 1; }
         return n;
     }
     const char *p = spec;
-    while (*p && n < MAX_DEVICES) {
+    while (*p && n < max_devs) {
         char *end;
-        long v = strtol(p, &end, 10);
-        if (end == p) break;
+        const long v = strtol(p, &end, 10);
+        if (end == p) return -1;
+        if (v < 0 || (visible > 0 && v >= visible)) return -1;
         devs[n++] = (int)v;
-        p = (*end == ',') ? end + 1 : end;
+        if (*end == ',') p = end + 1;
+        else if (*end == 0) break;
+        else return -1;
     }
     if (!n) { devs[0] = 0; n = 1; }
+    return n;
+}
+
+static int select_devices(int *devs)
+{
+    char spec[256];
+    pthread_mutex_lock(&g_spec_mu);
+    memcpy(spec, g_device_spec, sizeof(spec));
+    pthread_mutex_unlock(&g_spec_mu);
+    const char *sp = spec[0] ? spec : getenv("WFAGPU_DEVICES");
+    int visible = 0;
+    get_num_cuda_devices(&visible);
+    const int n = wfagpu_parse_devices(sp, visible, devs, MAX_DEVICES);
+    if (n < 0) fprintf(stderr, "[!] ERROR: bad device list \"%s\" (%d CUDA device(s) visible).\n", sp ? sp : "", visible);
     return n;
 }
 
@@ -70,24 +98,28 @@ typedef struct {
     wfa_alignment_result_t *res;
     wfa_alignment_options_t opt;
     bool cigar;
+    bool check;             /* check_correctness: validate every result (see check_chunk) */
+    bool pageable;          /* the caller's sequence buffer is not page-locked: stage every chunk */
     size_t n, chunk;
     size_t n_chunks;
-    size_t next_chunk;      /* guarded by mu */
     size_t next_from;       /* guarded by mu: first pair not handed out yet */
-    size_t first_chunk;     /* size of the first chunk of every device (ramp-up: its upload is not hidden) */
-    int first_left;         /* devices that have not taken their first chunk yet */
+    size_t first_chunk;     /* size of the first chunk of every worker (ramp-up: its upload is not hidden) */
     pthread_mutex_t mu;
     bool failed;
     bool verbose;
     bool host_cigar;        /* WFAGPU_HOST_CIGAR=1: print the CIGAR text on the host instead of the GPU */
     int decode_threads;
-    /* accumulated stats */
+    /* accumulated */
     wfagpu_run_stats_t stats;
+    uint64_t failed_pairs, checked, incorrect;
+    size_t first_failed[8];
+    int n_first_failed;
 } job_t;
 
 typedef struct {
     job_t *job;
     int dev;
+    bool first_taken;
 } worker_t;
 
 typedef struct {
@@ -106,17 +138,17 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-static bool take_chunk(job_t *j, size_t *from, size_t *n)
+static bool take_chunk(worker_t *w, size_t *from, size_t *n)
 {
+    job_t *j = w->job;
     bool ok = false;
     pthread_mutex_lock(&j->mu);
     if (!j->failed && j->next_from < j->n) {
         size_t want = j->chunk;
-        if (j->first_left > 0) { want = j->first_chunk; j->first_left--; }
+        if (!w->first_taken) { want = j->first_chunk; w->first_taken = true; }
         *from = j->next_from;
         *n = (*from + want <= j->n) ? want : j->n - *from;
         j->next_from += *n;
-        j->next_chunk++;
         ok = true;
     }
     pthread_mutex_unlock(&j->mu);
@@ -156,6 +188,17 @@ int wfagpu_pairs_from_metadata(sequence_pair_t *meta, size_t from, size_t n, siz
             fprintf(stderr, "[!] ERROR: sequence metadata is not laid out in increasing offsets.\n");
             return -1;
         }
+        if (((m[i].pattern_offset - base) | (m[i].text_offset - base)) & 3) {
+            /* the pack kernel reads 16-byte vectors and selects words: sequences start on 4-byte boundaries
+             * (the layout of lib/aligner.c:127-166 and of the readers) */
+            fprintf(stderr, "[!] ERROR: sequence %zu does not start on a 4-byte boundary of the batch.\n", from + i);
+            return -1;
+        }
+        if (m[i].pattern_len >= WFAGPU_MAX_SEQ_LEN || m[i].text_len >= WFAGPU_MAX_SEQ_LEN) {
+            fprintf(stderr, "[!] ERROR: pair %zu has a sequence of %u bases; the limit is %zu.\n", from + i,
+                    m[i].pattern_len > m[i].text_len ? m[i].pattern_len : m[i].text_len, (size_t)WFAGPU_MAX_SEQ_LEN - 1);
+            return -1;
+        }
         p->p_ascii = (uint32_t)(m[i].pattern_offset - base);
         p->t_ascii = (uint32_t)(m[i].text_offset - base);
         p->plen = m[i].pattern_len;
@@ -174,6 +217,20 @@ int wfagpu_pairs_from_metadata(sequence_pair_t *meta, size_t from, size_t n, siz
     return 0;
 }
 
+static void fill_plan(const job_t *j, bool cigar, wfagpu_plan_t *plan)
+{
+    memset(plan, 0, sizeof(*plan));
+    plan->x = j->opt.penalties.x;
+    plan->o = j->opt.penalties.o;
+    plan->e = j->opt.penalties.e;
+    plan->max_steps = j->opt.max_error;
+    plan->band = j->opt.band;
+    plan->band_width = j->opt.threads_per_block;
+    plan->with_cigar = cigar;
+    plan->threads_hint = j->opt.threads_per_block;
+    plan->workers_hint = j->opt.num_workers;
+}
+
 static int submit(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f)
 {
     if (f->pairs_cap < f->n) {
@@ -190,20 +247,68 @@ static int submit(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f)
     size_t base = 0, bytes = 0;
     if (wfagpu_pairs_from_metadata(j->meta, f->from, f->n, j->buf_size, f->pairs, &base, &bytes)) return -1;
     wfagpu_plan_t plan;
-    memset(&plan, 0, sizeof(plan));
-    plan.x = j->opt.penalties.x;
-    plan.o = j->opt.penalties.o;
-    plan.e = j->opt.penalties.e;
-    plan.max_steps = j->opt.max_error;
-    plan.band = j->opt.band;
-    plan.band_width = j->opt.threads_per_block;
-    plan.with_cigar = j->cigar;
-    plan.threads_hint = j->opt.threads_per_block;
-    plan.workers_hint = j->opt.num_workers;
-    if (wfagpu_device_upload(d, slot, j->buf + base, bytes, f->pairs, f->n)) return -1;
+    fill_plan(j, j->cigar, &plan);
+    const char *src = j->buf + base;
+    if (j->pageable) {
+        /* A caller that did not get its buffer from this library (calloc'ed like the reference's readers,
+         * utils/sequence_reader.c:73-78): copy the chunk into the slot's page-locked staging area with this
+         * worker's host threads, so that the upload is asynchronous DMA and overlaps the other slot's kernels. */
+        char *stage = wfagpu_device_staging(d, slot, bytes);
+        if (!stage) return -1;
+        const size_t blk = (size_t)1 << 20;
+        const long nblk = (long)((bytes + blk - 1) / blk);
+        #pragma omp parallel for schedule(static) num_threads(j->decode_threads) if (nblk > 8)
+        for (long b = 0; b < nblk; ++b) {
+            const size_t off = (size_t)b * blk;
+            memcpy(stage + off, src + off, off + blk <= bytes ? blk : bytes - off);
+        }
+        src = stage;
+    }
+    if (wfagpu_device_upload(d, slot, src, bytes, f->pairs, f->n)) return -1;
     if (wfagpu_device_align(d, slot, f->n, &plan, 0)) return -1;
     f->active = true;
     return 0;
+}
+
+/* check_correctness (the reference: lib/align.cu:258-326 validates the CIGAR with check_cigar_edit /
+ * check_affine_distance and compares the score with its CPU WFA).  There is no CPU aligner here: the CIGAR is
+ * validated on the host (it must be an alignment of the two sequences whose gap-affine cost is the reported
+ * score), and the score is compared with an INDEPENDENT GPU computation of the same chunk -- score only, through
+ * the one-diagonal-per-thread kernels without per-pair bounds, snapshots or provisioning hints
+ * (wfagpu_device_rescore).  A wrong optimum or a wrong path is counted as incorrect. */
+static void check_chunk(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f)
+{
+    const sequence_pair_t *m = j->meta + f->from;
+    const wfa_alignment_result_t *res = j->res + f->from;
+    int32_t *ref = (int32_t *)malloc(f->n * sizeof(int32_t));
+    wfagpu_plan_t plan;
+    fill_plan(j, false, &plan);
+    plan.band = 0;                                            /* the exact optimum, also for banded runs */
+    const bool have_ref = ref && wfagpu_device_rescore(d, slot, f->n, &plan, ref) == 0;
+    long bad = 0, sum = 0;
+    #pragma omp parallel for schedule(dynamic, 64) num_threads(j->decode_threads) reduction(+:bad,sum) if (f->n > 256)
+    for (long i = 0; i < (long)f->n; ++i) {
+        if (!(f->out[i].status & WFAGPU_ST_FINISHED)) continue;
+        bool ok = true;
+        if (j->cigar)
+            ok = wfagpu_check_result(j->buf + m[i].pattern_offset, m[i].pattern_len, j->buf + m[i].text_offset,
+                                     m[i].text_len, j->opt.penalties, res[i].error, res[i].cigar.buffer);
+        /* a banded score may legitimately exceed the optimum; an exact one must equal it */
+        if (have_ref && ref[i] >= 0 && (j->opt.band > 0 ? (long)res[i].error < ref[i] : (long)res[i].error != ref[i])) {
+            fprintf(stderr, "[!] ERROR: Incorrect distance (%zu). GPU=%u, independent GPU check=%d\n", f->from + (size_t)i,
+                    res[i].error, ref[i]);
+            ok = false;
+        }
+        if (!ok) bad++;
+        sum += res[i].error;
+    }
+    free(ref);
+    pthread_mutex_lock(&j->mu);
+    j->checked += f->n;
+    j->incorrect += (uint64_t)bad;
+    pthread_mutex_unlock(&j->mu);
+    fprintf(stderr, "(Batch from %zu) correct=%ld Incorrect=%ld Average score=%f%s\n", f->from, (long)f->n - bad, bad,
+            f->n ? (double)sum / (double)f->n : 0.0, have_ref ? "" : " (scores not re-computed)");
 }
 
 static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu_run_stats_t *acc)
@@ -235,11 +340,17 @@ static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu
 
     const sequence_pair_t *m = j->meta + f->from;
     wfa_alignment_result_t *res = j->res + f->from;
-    int bad = 0;
+    int bad = 0, failed = 0;
     const int nthreads = j->decode_threads;
-    #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) reduction(+:bad) if (f->n > 256)
+    #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) reduction(+:bad,failed) if (f->n > 256)
     for (long i = 0; i < (long)f->n; ++i) {
         const wfagpu_pair_out_t *o = &f->out[i];
+        if (o->status & WFAGPU_ST_FAILED) {
+            /* the GPU cannot finish this pair and nothing is computed on the CPU: never report a score for it */
+            res[i].error = UINT_MAX;
+            failed++;
+            continue;
+        }
         if (!(o->status & WFAGPU_ST_FINISHED)) { bad++; continue; }
         res[i].error = (unsigned int)o->distance;
         if (j->cigar && refs) {
@@ -251,10 +362,18 @@ static int collect(job_t *j, wfagpu_device_t *d, int slot, inflight_t *f, wfagpu
                 bad++;
         }
     }
+    if (failed) {
+        pthread_mutex_lock(&j->mu);
+        for (size_t i = 0; i < f->n && j->n_first_failed < 8; ++i)
+            if (f->out[i].status & WFAGPU_ST_FAILED) j->first_failed[j->n_first_failed++] = f->from + i;
+        j->failed_pairs += (uint64_t)failed;
+        pthread_mutex_unlock(&j->mu);
+    }
     if (bad) {
         fprintf(stderr, "[!] ERROR: %d alignments of the batch starting at %zu were not completed on the GPU.\n", bad, f->from);
         return -1;
     }
+    if (j->check) check_chunk(j, d, slot, f);
     if (j->verbose)
         fprintf(stderr, "[wfagpu] chunk from=%zu n=%zu: wait+download %.2f ms, text %.2f ms, host results %.2f ms (kernel %.2f ms)\n",
                 f->from, f->n, (t_b - t_a) * 1e3, (t_c - t_b) * 1e3, (now_s() - t_c) * 1e3, bs.ms_align);
@@ -275,7 +394,7 @@ static void *worker_main(void *arg)
     bool ok = true;
     while (ok) {
         size_t from, n;
-        const bool got = take_chunk(j, &from, &n);
+        const bool got = take_chunk(w, &from, &n);
         if (got) {
             fl[slot].from = from;
             fl[slot].n = n;
@@ -291,6 +410,7 @@ static void *worker_main(void *arg)
     }
     if (!ok) fail_job(j);
     for (int s = 0; s < 2; ++s) { free(fl[s].pairs); free(fl[s].out); }
+    wfagpu_device_release(d);
     pthread_mutex_lock(&j->mu);
     j->stats.gpu_align_ms += acc.gpu_align_ms;
     j->stats.gpu_pack_ms += acc.gpu_pack_ms;
@@ -303,18 +423,24 @@ static void *worker_main(void *arg)
     return NULL;
 }
 
-/* How the pair range is cut: chunks of at most `batch_size` pairs; with several GPUs at
- * least two chunks per GPU so that the tail balances; a chunk's ASCII stays below the
- * 32-bit offset limit of the device descriptors. */
+/* How the pair range is cut: chunks of at most `batch_size` pairs; at least two chunks per worker so that
+ * the tail balances and uploads hide behind kernels -- and when the caller left the batch size at "everything"
+ * (the reference's default), at least four per worker as long as a chunk keeps >= 1024 pairs; a chunk's ASCII
+ * stays below the 32-bit offset limit of the device descriptors. */
 void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii_span,
                         size_t *chunk_out, size_t *n_chunks_out)
 {
     size_t chunk = batch_size;
     if (n == 0) { *chunk_out = 0; *n_chunks_out = 0; return; }
     if (chunk == 0 || chunk > n) chunk = n;
+    if (n_devices < 1) n_devices = 1;
     if (n_devices > 1) {
         const size_t per = (n + (size_t)n_devices * 2 - 1) / ((size_t)n_devices * 2);
         if (per > 0 && per < chunk) chunk = per;
+    }
+    if (chunk == n || (n_devices > 1 && batch_size >= n)) {
+        const size_t per = (n + (size_t)n_devices * 4 - 1) / ((size_t)n_devices * 4);
+        if (per >= 1024 && per < chunk) chunk = per;
     }
     const size_t avg = ascii_span / n + 1;
     const size_t max_pairs = ((size_t)3 << 30) / avg;
@@ -326,12 +452,11 @@ void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii
 static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_alignment_result_t *res,
                     wfa_alignment_options_t opt, bool cigar, bool check)
 {
-    (void)check;
     const double t0 = now_s();
-    memset(&g_last_stats, 0, sizeof(g_last_stats));
-    g_last_ok = false;
+    memset(&t_last_stats, 0, sizeof(t_last_stats));
+    t_last_ok = false;
     if (!buf || !meta || !res) { fprintf(stderr, "[!] ERROR: invalid buffers.\n"); return; }
-    if (opt.num_alignments == 0) { g_last_ok = true; return; }
+    if (opt.num_alignments == 0) { t_last_ok = true; return; }
     if (opt.penalties.x < 1 || opt.penalties.e < 1 || opt.penalties.o < 0) {
         /* x = 0 or e = 0 make a wavefront depend on itself; the reference reads
          * half-written memory in that case (lib/kernels/sequence_alignment_kernel.cu:149-152) */
@@ -339,29 +464,30 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
         return;
     }
     int devs[MAX_DEVICES];
-    const int ndev = parse_devices(devs);
+    const int ndev = select_devices(devs);
+    if (ndev < 1) return;
 
     job_t job;
     memset(&job, 0, sizeof(job));
     job.buf = buf; job.buf_size = buf_size; job.meta = meta; job.res = res; job.opt = opt; job.cigar = cigar;
+    job.check = check;
     job.n = opt.num_alignments;
+    job.pageable = !wfagpu_host_is_pinned(buf);
     const size_t span = meta[job.n - 1].text_offset + meta[job.n - 1].text_len + 1 - meta[0].pattern_offset;
     size_t chunk = 0, n_chunks_unused = 0;
     wfagpu_plan_chunks(job.n, opt.batch_size, ndev, span, &chunk, &n_chunks_unused);
     job.chunk = chunk;
     job.n_chunks = (job.n + chunk - 1) / chunk;
-    /* Ramp-up: the upload of a device's first chunk cannot hide behind kernels, so that chunk is a
-     * quarter of the others (WFAGPU_RAMP=0 disables) -- only for streams of at least four chunks per device
+    /* Ramp-up: the upload of a worker's first chunk cannot hide behind kernels, so that chunk is a
+     * quarter of the others (WFAGPU_RAMP=0 disables) -- only for streams of at least four chunks per worker
      * (measured on B200, 10 kbp / 5 %: 32768 pairs in chunks of 4096 226.8 k -> 234.4 k aln/s; with only two
      * chunks per call the extra chunk costs more than the hidden upload saves: 223 k -> 219 k). */
     job.first_chunk = chunk;
-    job.first_left = 0;
     {
         const char *rp = getenv("WFAGPU_RAMP");
         const int ramp = rp ? atoi(rp) : 4;
-        if (ramp > 1 && job.n_chunks >= (size_t)4 * (size_t)ndev && chunk >= 64) {
+        if (ramp > 1 && job.n_chunks >= (size_t)4 * (size_t)ndev && chunk / (size_t)ramp >= 16) {
             job.first_chunk = chunk / (size_t)ramp;
-            job.first_left = ndev;
             job.n_chunks += (size_t)ndev;         /* upper bound: used to size the worker pool only */
         }
     }
@@ -377,12 +503,12 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     job.verbose = vb && atoi(vb) != 0;
     const char *hc = getenv("WFAGPU_HOST_CIGAR");
     job.host_cigar = hc && atoi(hc) != 0;
-    if (!job.host_cigar && job.decode_threads > 4) job.decode_threads = 4;   /* only memcpy of finished text is left */
+    if (!job.host_cigar && !job.check && job.decode_threads > 4) job.decode_threads = 4;   /* only memcpy of finished text is left */
 
     const int nworkers = (size_t)ndev < job.n_chunks ? ndev : (int)job.n_chunks;
     worker_t workers[MAX_DEVICES];
     pthread_t th[MAX_DEVICES];
-    for (int i = 0; i < nworkers; ++i) { workers[i].job = &job; workers[i].dev = devs[i]; }
+    for (int i = 0; i < nworkers; ++i) { workers[i].job = &job; workers[i].dev = devs[i]; workers[i].first_taken = false; }
     if (nworkers == 1) {
         worker_main(&workers[0]);
     } else {
@@ -390,10 +516,20 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
         for (int i = 0; i < nworkers; ++i) pthread_join(th[i], NULL);
     }
     pthread_mutex_destroy(&job.mu);
-    g_last_stats = job.stats;
-    g_last_stats.devices = nworkers;
-    g_last_stats.wall_s = now_s() - t0;
-    g_last_ok = !job.failed;
+    t_last_stats = job.stats;
+    t_last_stats.devices = nworkers;
+    t_last_stats.failed_pairs = job.failed_pairs;
+    t_last_stats.checked = job.checked;
+    t_last_stats.incorrect = job.incorrect;
+    t_last_stats.staged = job.pageable ? 1 : 0;
+    t_last_stats.wall_s = now_s() - t0;
+    t_last_ok = !job.failed && job.failed_pairs == 0;
+    if (job.failed_pairs) {
+        fprintf(stderr, "[!] ERROR: %llu pair(s) could not be aligned on the GPU (error = UINT_MAX, no CIGAR); first indices:",
+                (unsigned long long)job.failed_pairs);
+        for (int i = 0; i < job.n_first_failed; ++i) fprintf(stderr, " %zu", job.first_failed[i]);
+        fprintf(stderr, "\n");
+    }
     if (job.failed) fprintf(stderr, "[!] ERROR: alignment failed on the GPU (no CPU fallback exists in this library).\n");
 }
 

@@ -15,6 +15,14 @@
 #include <string.h>
 #include "wfagpu_b200.h"
 
+static long file_size(FILE *fp)
+{
+    long sz = -1;
+    if (fseek(fp, 0, SEEK_END) == 0) sz = ftell(fp);
+    rewind(fp);
+    return sz;
+}
+
 static size_t chomp(char *line, ssize_t n)
 {
     while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
@@ -25,6 +33,11 @@ long wfagpu_read_seq_file(wfagpu_aligner_t *aligner, const char *path, size_t ma
 {
     FILE *fp = fopen(path, "r");
     if (!fp) { fprintf(stderr, "[!] ERROR: Could not open %s\n", path); return -1; }
+    if (max_pairs == 0) {
+        /* one page-locked allocation for the whole file instead of geometric growth */
+        const long fsz = file_size(fp);
+        if (fsz > 0) wfagpu_reserve(aligner, (size_t)fsz + (size_t)fsz / 16 + 4096, 0);
+    }
     char *line = NULL, *pattern = NULL;
     size_t cap = 0, lineno = 0;
     ssize_t n;
@@ -92,6 +105,10 @@ long wfagpu_read_fasta_files(wfagpu_aligner_t *aligner, const char *query_path, 
         if (t.fp) fclose(t.fp);
         return -1;
     }
+    if (max_pairs == 0) {
+        const long a = file_size(q.fp), b = file_size(t.fp);
+        if (a > 0 && b > 0) wfagpu_reserve(aligner, (size_t)(a + b) + (size_t)(a + b) / 16 + 4096, 0);
+    }
     char *qs = NULL, *ts = NULL;
     size_t qc = 0, tc = 0;
     long pairs = 0;
@@ -139,46 +156,148 @@ bool wfagpu_check_result(const char *pattern, size_t plen, const char *text, siz
 }
 
 
-/* The reference's two generic validators under their own names and argument order (text first):
- * utils/verification.h:37-49.  Exported by the reference library and used by its `-c` path. */
-static bool walk_cigar(const char *text, const char *pattern, size_t tlen, size_t plen, const char *cigar,
-                       const affine_penalties_t *pen, unsigned long *score_out)
+/* ---------------------------------------------------------------------------------------------
+ * The reference library's validators under their own names, argument order (text first) and input format
+ * (utils/verification.h:37-58).  The reference hands them the UNROLLED op string that its recover_cigar
+ * produces ("MMMXMMIIM", one letter per column; lib/align.cu:284-293); results[i].cigar.buffer holds the
+ * run-length text ("3M1X2M2I1M").  Both spellings are accepted: a CIGAR that starts with a digit is read as
+ * run-length text, anything else letter by letter.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct { const char *c; unsigned long left; char op; bool rle; bool bad; } cigar_it_t;
+
+static void cig_begin(cigar_it_t *it, const char *cigar)
 {
-    size_t v = 0, h = 0;
-    unsigned long score = 0;
-    const char *c = cigar;
-    if (!c || !text || !pattern) return false;
-    while (*c) {
-        unsigned long rep = 0;
-        if (*c < '0' || *c > '9') return false;
-        while (*c >= '0' && *c <= '9') rep = rep * 10 + (unsigned long)(*c++ - '0');
-        const char op = *c++;
-        if (op == 'M' || op == 'X') {
-            if (v + rep > plen || h + rep > tlen) return false;
-            for (unsigned long i = 0; i < rep; ++i)
-                if ((pattern[v + i] == text[h + i]) != (op == 'M')) return false;
-            v += rep; h += rep;
-            if (op == 'X' && pen) score += rep * (unsigned long)pen->x;
-        } else if (op == 'I') { h += rep; if (pen) score += (unsigned long)pen->o + rep * (unsigned long)pen->e; }
-        else if (op == 'D') { v += rep; if (pen) score += (unsigned long)pen->o + rep * (unsigned long)pen->e; }
-        else return false;
-        if (v > plen || h > tlen) return false;
-    }
-    if (score_out) *score_out = score;
-    return v == plen && h == tlen;
+    it->c = cigar; it->left = 0; it->op = 0; it->bad = false;
+    it->rle = cigar && cigar[0] >= '0' && cigar[0] <= '9';
+}
+/* next column of the alignment: 'M', 'X', 'I', 'D'; 0 at the end (or on malformed run-length text: it->bad) */
+static char cig_next(cigar_it_t *it)
+{
+    if (it->left) { it->left--; return it->op; }
+    if (!it->c || !*it->c) return 0;
+    if (!it->rle) return *it->c++;
+    unsigned long rep = 0;
+    if (*it->c < '0' || *it->c > '9') { it->bad = true; return 0; }
+    while (*it->c >= '0' && *it->c <= '9') rep = rep * 10 + (unsigned long)(*it->c++ - '0');
+    it->op = *it->c ? *it->c++ : 0;
+    if (!it->op || rep == 0) { it->bad = true; return 0; }
+    it->left = rep - 1;
+    return it->op;
 }
 
 bool check_cigar_edit(const char *text, const char *pattern, const int tlen, const int plen, const char *curr_cigar)
 {
-    if (tlen < 0 || plen < 0) return false;
-    return walk_cigar(text, pattern, (size_t)tlen, (size_t)plen, curr_cigar, NULL, NULL);
+    if (!curr_cigar || !text || !pattern || tlen < 0 || plen < 0) return false;
+    long h = 0, v = 0;
+    cigar_it_t it;
+    cig_begin(&it, curr_cigar);
+    for (char op; (op = cig_next(&it)) != 0;) {
+        switch (op) {
+        case 'M':
+            if (v >= plen || h >= tlen || pattern[v] != text[h]) return false;
+            ++v; ++h;
+            break;
+        case 'X':
+            if (v >= plen || h >= tlen || pattern[v] == text[h]) return false;
+            ++v; ++h;
+            break;
+        case 'I': ++h; break;
+        case 'D': ++v; break;
+        default:                      /* the reference skips letters it does not know (verification.c:71-73) */
+            if (it.rle) return false;
+            break;
+        }
+        if (v > plen || h > tlen) return false;
+    }
+    return !it.bad && v == plen && h == tlen;
 }
 
 bool check_affine_distance(const char *text, const char *pattern, const int tlen, const int plen, const int distance,
                            const affine_penalties_t penalties, const char *cigar)
 {
-    unsigned long score = 0;
-    if (tlen < 0 || plen < 0 || distance < 0) return false;
-    if (!walk_cigar(text, pattern, (size_t)tlen, (size_t)plen, cigar, &penalties, &score)) return false;
-    return score == (unsigned long)distance;
+    (void)text; (void)pattern; (void)tlen; (void)plen;      /* like the reference, only the op string is scored */
+    if (!cigar || distance < 0) return false;
+    long score = 0;
+    char gap = 0;                                           /* 'I' / 'D' while inside a gap of that kind */
+    cigar_it_t it;
+    cig_begin(&it, cigar);
+    for (char op; (op = cig_next(&it)) != 0;) {
+        if (op == 'I' || op == 'D') {
+            score += (gap == op) ? penalties.e : penalties.o + penalties.e;
+            gap = op;
+            /* run-length text prints two same-type gaps that only a gap-close separates as two runs ("1I1I") */
+            if (it.rle && it.left == 0) gap = 0;
+        } else {
+            gap = 0;
+            if (op == 'X') score += penalties.x;
+            else if (op != 'M' && it.rle) return false;
+        }
+    }
+    return !it.bad && score == (long)distance;
+}
+
+/* Unrolled op string ("MMXMMI...", malloc'ed, caller frees) of run-length CIGAR text: what the reference's
+ * recover_cigar returns for the same alignment. */
+char *wfagpu_unroll_cigar(const char *rle)
+{
+    if (!rle) return NULL;
+    size_t n = 0;
+    cigar_it_t it;
+    cig_begin(&it, rle);
+    if (!it.rle && rle[0]) return strdup(rle);
+    while (cig_next(&it)) ++n;
+    if (it.bad) return NULL;
+    char *out = (char *)malloc(n + 1);
+    if (!out) return NULL;
+    cig_begin(&it, rle);
+    size_t i = 0;
+    for (char op; (op = cig_next(&it)) != 0;) out[i++] = op;
+    out[i] = 0;
+    return out;
+}
+
+/* recover_cigar (utils/verification.h:52-58): unrolled op string from a backtrace chain in the REFERENCE's own
+ * format -- `offloaded_backtraces_array[num_bt_blocks - 1]` is the oldest full word, `final_backtrace` the last,
+ * 16 two-bit ops per word filled from the least significant end, the op of a word's first step in its highest
+ * used bits.  This library's kernels do not produce such chains (they emit a flat 2-bit op stream, see
+ * wfagpu_ops_to_cigar); the function is kept for callers that hold reference-format results. */
+static long common_prefix(const char *pattern, long plen, const char *text, long tlen, long v, long h)
+{
+    long n = 0;
+    while (v + n < plen && h + n < tlen && pattern[v + n] == text[h + n]) ++n;
+    return n;
+}
+
+char *recover_cigar(const char *text, const char *pattern, const size_t tlen, const size_t plen,
+                    wfa_backtrace_t final_backtrace, wfa_backtrace_t *offloaded_backtraces_array,
+                    alignment_result_t result)
+{
+    char *out = (char *)calloc(tlen + plen + 1, 1);
+    if (!out) return NULL;
+    size_t w = 0;
+    long k = 0, off = 0;
+    bool in_gap = false;
+    for (int blk = result.num_bt_blocks; blk >= 0; --blk) {
+        const uint32_t word = blk > 0 ? offloaded_backtraces_array[blk - 1].backtrace : final_backtrace.backtrace;
+        const int used = word ? 16 - (__builtin_clz(word) >> 1) : 0;
+        for (int i = used - 1; i >= 0; --i) {
+            if (!in_gap) {
+                const long m = common_prefix(pattern, (long)plen, text, (long)tlen, off - k, off);
+                for (long j = 0; j < m && w < tlen + plen; ++j) out[w++] = 'M';
+                off += m;
+            }
+            const unsigned op = (word >> (2 * i)) & 3u;
+            if (op == OP_DEL) { in_gap = true; --k; if (w < tlen + plen) out[w++] = 'D'; }
+            else if (op == OP_INS) { in_gap = true; ++k; ++off; if (w < tlen + plen) out[w++] = 'I'; }
+            else if (op == OP_SUB) {
+                if (in_gap) in_gap = false;                 /* gap-close delimiter */
+                else { ++off; if (w < tlen + plen) out[w++] = 'X'; }
+            }
+        }
+    }
+    if (!in_gap) {
+        const long m = common_prefix(pattern, (long)plen, text, (long)tlen, off - k, off);
+        for (long j = 0; j < m && w < tlen + plen; ++j) out[w++] = 'M';
+    }
+    return out;
 }

@@ -50,7 +50,8 @@ class AlignerStruct(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [("wall_s", C.c_double), ("gpu_align_ms", C.c_double), ("gpu_pack_ms", C.c_double),
                 ("launches", C.c_uint64), ("redispatched", C.c_uint64), ("ascii_pairs", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("devices", C.c_int)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("devices", C.c_int), ("staged", C.c_int),
+                ("failed_pairs", C.c_uint64), ("checked", C.c_uint64), ("incorrect", C.c_uint64)]
 
 
 class Step(C.Structure):
@@ -70,7 +71,7 @@ class BatchStats(C.Structure):
     _fields_ = [("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("launches", C.c_uint32), ("redispatched", C.c_uint32),
                 ("ascii_pairs", C.c_uint32), ("cells", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("ms_wavefront", C.c_float), ("reserved0", C.c_float)]
+                ("ms_wavefront", C.c_float), ("failed_pairs", C.c_uint32)]
 
 
 class DevPair(C.Structure):
@@ -91,6 +92,8 @@ EXPORTS = [
     "wfagpu_pairs_from_metadata", "wfagpu_reset_results", "wfagpu_read_seq_file", "wfagpu_read_fasta_files",
     "wfagpu_check_result", "wfagpu_last_launch_ok", "wfagpu_plan_chunks",
     "check_cigar_edit", "check_affine_distance", "wfagpu_cigar_append", "wfagpu_device_download_text",
+    "recover_cigar", "wfagpu_unroll_cigar", "wfagpu_device_release", "wfagpu_device_rescore", "wfagpu_device_staging",
+    "wfagpu_host_is_pinned", "wfagpu_host_alloc", "wfagpu_host_free", "wfagpu_reserve", "wfagpu_parse_devices",
 ]
 
 _lib = None
@@ -156,6 +159,21 @@ def load():
                                          P(C.c_size_t), P(C.c_uint32)]
     L.wfagpu_device_last_stats.argtypes = [C.c_void_p, C.c_int, P(BatchStats)]
     L.wfagpu_device_sm_count.argtypes = [C.c_void_p]
+    L.wfagpu_device_release.argtypes = [C.c_void_p]
+    L.wfagpu_device_release.restype = None
+    L.wfagpu_device_rescore.argtypes = [C.c_void_p, C.c_int, C.c_size_t, P(Plan), P(C.c_int32)]
+    L.wfagpu_host_is_pinned.argtypes = [C.c_void_p]
+    L.wfagpu_unroll_cigar.argtypes = [C.c_char_p]
+    L.wfagpu_unroll_cigar.restype = C.c_void_p
+    L.check_cigar_edit.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+    L.check_cigar_edit.restype = C.c_bool
+    L.check_affine_distance.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, AffinePenalties, C.c_char_p]
+    L.check_affine_distance.restype = C.c_bool
+    L.wfagpu_parse_devices.argtypes = [C.c_char_p, C.c_int, P(C.c_int), C.c_int]
+    L.launch_alignments.argtypes = [C.c_void_p, C.c_size_t, P(SequencePair), P(AlignmentResult), AlignmentOptions, C.c_bool]
+    L.launch_alignments.restype = None
+    L.launch_alignments_distance.argtypes = [C.c_void_p, C.c_size_t, P(SequencePair), P(AlignmentResult), AlignmentOptions, C.c_bool]
+    L.launch_alignments_distance.restype = None
     L.wfagpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.wfagpu_host_unregister.argtypes = [C.c_void_p]
     L.wfagpu_pairs_from_metadata.argtypes = [P(SequencePair), C.c_size_t, C.c_size_t, C.c_size_t, P(DevPair),
@@ -249,9 +267,23 @@ class Aligner:
     def reset_results(self):
         self.L.wfagpu_reset_results(C.byref(self.s))
 
+    def host_buffer_pinned(self):
+        """True when the sequence buffer is page-locked (wfagpu_initialize_aligner allocates it that way)."""
+        return bool(self.L.wfagpu_host_is_pinned(self.s.sequences_buffer))
+
     def pin_host_buffers(self):
-        """Page-lock the sequence buffer so H2D copies are asynchronous DMA."""
+        """Page-lock the sequence buffer so H2D copies are asynchronous DMA (a no-op for the aligner's own buffer)."""
+        if self.host_buffer_pinned():
+            return True
         return self.L.wfagpu_host_register(self.s.sequences_buffer, self.s.sequences_buffer_len) == 0
+
+    def align_checked(self):
+        """launch_alignments* with check_correctness = true; returns (checked, incorrect)."""
+        o = self.s.alignment_options
+        fn = self.L.launch_alignments if o.compute_cigar else self.L.launch_alignments_distance
+        fn(self.s.sequences_buffer, self.s.sequences_buffer_len, self.s.sequences_metadata, self.s.results, o, True)
+        st = self.run_stats()
+        return st["checked"], st["incorrect"]
 
     def unpin_host_buffers(self):
         self.L.wfagpu_host_unregister(self.s.sequences_buffer)
@@ -325,3 +357,17 @@ class ResidentBatch:
 
     def sm_count(self):
         return self.L.wfagpu_device_sm_count(self.dev)
+
+    def rescore(self, plan=None):
+        """Independent score-only re-computation of the resident batch (the -c path)."""
+        plan = plan or self.plan()
+        out = (C.c_int32 * self.n)()
+        if self.L.wfagpu_device_rescore(self.dev, self.slot, self.n, C.byref(plan), out):
+            raise RuntimeError("wfagpu_device_rescore failed")
+        return list(out)
+
+    def release(self):
+        """Hand the leased device context back to the pool."""
+        if self.dev:
+            self.L.wfagpu_device_release(self.dev)
+            self.dev = None
