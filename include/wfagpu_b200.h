@@ -104,6 +104,9 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     float ms_wavefront;       /* the first pass's wavefront kernel alone (0 if it ran in several sub-launches) */
     uint32_t failed_pairs;    /* pairs reported as WFAGPU_ST_FAILED                                            */
+    uint32_t pending_pairs;   /* after wfagpu_device_wait: pairs the first pass left to the re-dispatch tier   */
+    uint32_t n_cap, cta_threads, ctas, d_end; /* launch shape of the first pass: ring half width, CTA size, grid, score limit */
+    uint32_t reserved1;
 } wfagpu_batch_stats_t;
 
 /* Leases a context of CUDA device `dev`: an idle one from the pool (with its grown buffers) or a new one; the
@@ -186,6 +189,10 @@ void wfagpu_set_devices(const char *spec);
 /* Chunking of a job over `n_devices` GPUs (pure function, used by launch_alignments*). */
 void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii_span,
                         size_t *chunk_out, size_t *n_chunks_out);
+
+/* Host threads this library may use per call (result loop, staging copies, generators); 0 = OpenMP default.
+ * torchrun pins OMP_NUM_THREADS=1 per rank: a rank that works alone can lift that. */
+void wfagpu_set_host_threads(int n);
 
 /* Stats of the last launch_alignments* call (summed over batches/devices). */
 typedef struct {

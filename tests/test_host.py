@@ -288,9 +288,10 @@ def test_chunk_plan(lib):
     chunk, n = C.c_size_t(), C.c_size_t()
     f = lambda *a: (lib.wfagpu_plan_chunks(*a, C.byref(chunk), C.byref(n)), (chunk.value, n.value))[1]
     assert f(100, 100, 1, 10**6) == (100, 1)                                 # small call: one chunk
-    assert f(8192, 8192, 1, 8192 * 20000) == (2048, 4)                       # default batch size: four chunks per worker
+    assert f(8192, 8192, 1, 8192 * 20000) == (4096, 2)                       # default batch size: two chunks per worker
     assert f(8192, 1000, 1, 8192 * 20000) == (1000, 9)                       # the caller's batch size is an upper bound
-    assert f(8192, 8192, 2, 8192 * 20000) == (1024, 8)
+    assert f(8192, 8192, 2, 8192 * 20000) == (2048, 4)
+    assert f(100000, 100000, 1, 100000 * 20000) == (12500, 8)                # long streams: eight chunks per worker
     assert f(3000, 3000, 2, 3000 * 300) == (750, 4)                          # several GPUs: at least two chunks each
     assert f(4, 4, 8, 4000)[0] >= 1
     c, k = f(10**6, 10**6, 1, 10**6 * 20000)                                 # a chunk's ASCII stays below 3 GiB

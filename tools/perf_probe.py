@@ -28,4 +28,4 @@ st = rb.stats()
 best = min(ms)
 print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("WFAGPU_")}, "pairs": n, "len": L, "err": err,
                   "cigar": cigar, "align_ms": [round(m, 2) for m in ms], "wavefront_ms": round(min(wf), 2), "pairs_per_s": round(n / (best / 1e3), 1),
-                  "redispatched": st["redispatched"], "cells": st["cells"]}))
+                  "redispatched": st["redispatched"], "cells": st["cells"], "n_cap": st["n_cap"], "cta_threads": st["cta_threads"], "ctas": st["ctas"], "d_end": st["d_end"]}))

@@ -194,6 +194,7 @@ struct wfagpu_device {
     bool device_text = true;   /* WFAGPU_HOST_CIGAR=1 leaves the text to the host */
     bool leased = false;       /* handed out by wfagpu_device_open and not released yet */
     bool independent = false;  /* wfagpu_device_rescore in progress: do not learn hints from it */
+    int hint_margin_pm = 83, hint_min_pm = 31;   /* provisioning margins over the last batch's largest score, per mille */
     int max_steps_cap = 60000; /* most wavefront steps a pair may take (WFAGPU_MAX_STEPS_CAP lowers it: tests) */
 };
 
@@ -296,6 +297,8 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
     d->force_large = env_int("WFAGPU_FORCE_LARGE", 0) != 0;
     d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;
+    d->hint_margin_pm = std::max(0, env_int("WFAGPU_HINT_MARGIN_PM", 83));
+    d->hint_min_pm = std::min(d->hint_margin_pm, std::max(0, env_int("WFAGPU_HINT_MIN_PM", 31)));
     d->max_steps_cap = std::min(60000, std::max(16, env_int("WFAGPU_MAX_STEPS_CAP", 60000)));
     d->leased = true;
     g_devices.push_back(d);
@@ -676,7 +679,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     int d_want = d_full;
     bool hinted = false;
     if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e) {
-        d_want = (int)std::min<long long>((long long)d->hint_dist + d->hint_dist / 12 + 8, d_full - 1) + 1;
+        d_want = (int)std::min<long long>((long long)d->hint_dist + (long long)d->hint_dist * d->hint_margin_pm / 1000 + 8, d_full - 1) + 1;
         hinted = d_want < d_full;
     }
     /* no pair of the batch can score more than substitutions all along the shorter sequence plus one
@@ -707,7 +710,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     /* with a hint, rings for hint + 3 % are enough for (almost) every pair */
     int n_min = n_want;
     if (hinted && plan.band <= 0)
-        n_min = std::min(n_want, n_need((int)std::min<long long>((long long)d->hint_dist + d->hint_dist / 32 + 4, d_full - 1) + 1));
+        n_min = std::min(n_want, n_need((int)std::min<long long>((long long)d->hint_dist + (long long)d->hint_dist * d->hint_min_pm / 1000 + 4, d_full - 1) + 1));
     const bool banded = plan.band > 0;
     LaunchCfg c{};
     int rc = 0;
@@ -943,6 +946,12 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         }
     }
     tr.mark("tb");
+    if (first_pass) {
+        s.stats.n_cap = (uint32_t)c.n_cap;
+        s.stats.cta_threads = (uint32_t)(c.group_threads * c.groups_per_cta);
+        s.stats.ctas = (uint32_t)c.ctas;
+        s.stats.d_end = (uint32_t)d_end;
+    }
     s.last_d_end = std::max(s.last_d_end, d_end);
     s.text_queued = false;
     return 0;
@@ -1199,6 +1208,12 @@ extern "C" int wfagpu_device_wait(wfagpu_device_t *d, int slot, float *ms_pack, 
     if (ms_align) cudaEventElapsedTime(ms_align, s.ev[3], s.ev[4]);
     s.stats.ms_wavefront = 0;
     if (s.wf_timed) cudaEventElapsedTime(&s.stats.ms_wavefront, s.ev[6], s.ev[7]);
+    /* pairs the timed pass left for the re-dispatch tier / the byte-compare kernel (both run in download()) */
+    if (s.n) {
+        CK(cudaMemcpyAsync(s.h_counters.p, s.counters.p, CTR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        s.stats.pending_pairs = s.h_counters.p[CTR_RETRY] + s.h_counters.p[CTR_ASCII];
+    }
     if (s.n && d->use_hint) {
         /* read the result records back (16 B per pair) so that a re-run of the resident
          * batch is provisioned like the next batch of a stream would be */

@@ -41,6 +41,8 @@ void wfagpu_set_devices(const char *spec)
     pthread_mutex_unlock(&g_spec_mu);
 }
 
+void wfagpu_set_host_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 void wfagpu_last_run_stats(wfagpu_run_stats_t *st) { if (st) *st = t_last_stats; }
 bool wfagpu_last_launch_ok(void) { return t_last_ok; }
 
@@ -424,8 +426,9 @@ static void *worker_main(void *arg)
 }
 
 /* How the pair range is cut: chunks of at most `batch_size` pairs; at least two chunks per worker so that
- * the tail balances and uploads hide behind kernels -- and when the caller left the batch size at "everything"
- * (the reference's default), at least four per worker as long as a chunk keeps >= 1024 pairs; a chunk's ASCII
+ * uploads hide behind kernels and the tail balances -- eight per worker once a worker's share reaches 32768
+ * pairs, as long as a chunk keeps >= 1024 pairs (measured on B200, one 8192 x 10 kbp call: 2 x 4096 32.5 ms,
+ * 4 x 2048 33.5 ms, 8 x 1024 37.6 ms: every launch has a ragged tail of one pair's run time); a chunk's ASCII
  * stays below the 32-bit offset limit of the device descriptors. */
 void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii_span,
                         size_t *chunk_out, size_t *n_chunks_out)
@@ -434,17 +437,14 @@ void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii
     if (n == 0) { *chunk_out = 0; *n_chunks_out = 0; return; }
     if (chunk == 0 || chunk > n) chunk = n;
     if (n_devices < 1) n_devices = 1;
-    if (n_devices > 1) {
-        const size_t per = (n + (size_t)n_devices * 2 - 1) / ((size_t)n_devices * 2);
-        if (per > 0 && per < chunk) chunk = per;
-    }
-    if (chunk == n || (n_devices > 1 && batch_size >= n)) {
-        const size_t per = (n + (size_t)n_devices * 4 - 1) / ((size_t)n_devices * 4);
-        if (per >= 1024 && per < chunk) chunk = per;
-    }
+    const size_t share = (n + (size_t)n_devices - 1) / (size_t)n_devices;
+    const size_t parts = share >= 32768 ? 8 : 2;
+    const size_t per = (share + parts - 1) / parts;
+    if (per < chunk && (per >= 1024 || n_devices > 1)) chunk = per;
     const size_t avg = ascii_span / n + 1;
     const size_t max_pairs = ((size_t)3 << 30) / avg;
     if (max_pairs > 0 && chunk > max_pairs) chunk = max_pairs;
+    if (chunk == 0) chunk = 1;
     *chunk_out = chunk;
     *n_chunks_out = (n + chunk - 1) / chunk;
 }
@@ -478,16 +478,25 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     wfagpu_plan_chunks(job.n, opt.batch_size, ndev, span, &chunk, &n_chunks_unused);
     job.chunk = chunk;
     job.n_chunks = (job.n + chunk - 1) / chunk;
-    /* Ramp-up: the upload of a worker's first chunk cannot hide behind kernels, so that chunk is a
-     * quarter of the others (WFAGPU_RAMP=0 disables) -- only for streams of at least four chunks per worker
-     * (measured on B200, 10 kbp / 5 %: 32768 pairs in chunks of 4096 226.8 k -> 234.4 k aln/s; with only two
-     * chunks per call the extra chunk costs more than the hidden upload saves: 223 k -> 219 k). */
+    /* Ramp-up: the upload of a worker's first chunk cannot hide behind kernels, so that chunk is smaller than the
+     * others -- but never so small that its kernels leave the GPU half empty: at least 10 pairs per SM
+     * (measured on B200, 8192 x 10 kbp: first chunk 512 of 2048 -> 37.7 ms per call, no ramp -> 33.5 ms).
+     * WFAGPU_RAMP=0 disables, WFAGPU_FIRST_CHUNK=n sets the size. */
     job.first_chunk = chunk;
     {
         const char *rp = getenv("WFAGPU_RAMP");
+        const char *fc = getenv("WFAGPU_FIRST_CHUNK");
         const int ramp = rp ? atoi(rp) : 4;
-        if (ramp > 1 && job.n_chunks >= (size_t)4 * (size_t)ndev && chunk / (size_t)ramp >= 16) {
-            job.first_chunk = chunk / (size_t)ramp;
+        size_t first = chunk;
+        if (fc && atol(fc) > 0) first = (size_t)atol(fc);
+        else if (ramp > 1 && job.n_chunks >= (size_t)4 * (size_t)ndev) {
+            const int sms = get_cuda_SM_count(devs[0]);
+            const size_t floor_pairs = (size_t)10 * (size_t)(sms > 0 ? sms : 148);
+            first = chunk / (size_t)ramp;
+            if (first < floor_pairs) first = floor_pairs;
+        }
+        if (first < chunk && first >= 1) {
+            job.first_chunk = first;
             job.n_chunks += (size_t)ndev;         /* upper bound: used to size the worker pool only */
         }
     }

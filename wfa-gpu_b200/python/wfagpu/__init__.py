@@ -71,7 +71,9 @@ class BatchStats(C.Structure):
     _fields_ = [("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("launches", C.c_uint32), ("redispatched", C.c_uint32),
                 ("ascii_pairs", C.c_uint32), ("cells", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("ms_wavefront", C.c_float), ("failed_pairs", C.c_uint32)]
+                ("ms_wavefront", C.c_float), ("failed_pairs", C.c_uint32), ("pending_pairs", C.c_uint32),
+                ("n_cap", C.c_uint32), ("cta_threads", C.c_uint32), ("ctas", C.c_uint32), ("d_end", C.c_uint32),
+                ("reserved1", C.c_uint32)]
 
 
 class DevPair(C.Structure):
@@ -94,6 +96,7 @@ EXPORTS = [
     "check_cigar_edit", "check_affine_distance", "wfagpu_cigar_append", "wfagpu_device_download_text",
     "recover_cigar", "wfagpu_unroll_cigar", "wfagpu_device_release", "wfagpu_device_rescore", "wfagpu_device_staging",
     "wfagpu_host_is_pinned", "wfagpu_host_alloc", "wfagpu_host_free", "wfagpu_reserve", "wfagpu_parse_devices",
+    "wfagpu_set_host_threads",
 ]
 
 _lib = None
@@ -292,6 +295,10 @@ class Aligner:
         st = RunStats()
         self.L.wfagpu_last_run_stats(C.byref(st))
         return {k: getattr(st, k) for k, _ in RunStats._fields_}
+
+
+def set_host_threads(n):
+    load().wfagpu_set_host_threads(int(n))
 
 
 def set_devices(spec):
