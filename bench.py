@@ -328,6 +328,12 @@ def run_configs(wfagpu):
     refcpu = RefCPU() if RefCPU.available() else None
     out = {}
 
+    def release(a):
+        """Every configuration starts from an empty device: pooled contexts keep their grown buffers (tens of GB of
+        snapshot arenas after cfg 4), and a configuration that finds little free memory gets fewer resident CTAs."""
+        a.destroy()
+        wfagpu.load().wfagpu_device_close_all()
+
     def entry(a, dt, st, parity, extra=None):
         e = {"pairs": a.num_pairs, "e2e_alignments_per_s": round(a.num_pairs / dt, 1), "e2e_gcups": round(gcells(a) / dt / 1e9, 1),
              "wall_ms": round(dt * 1e3, 2), "redispatched": int(st["redispatched"]), "launches": int(st["launches"]),
@@ -340,17 +346,17 @@ def run_configs(wfagpu):
     a = make_aligner(wfagpu, 0xB2000001, 10000, 150, 0.02, 0.02, PEN, cigar=True)
     dt, st = time_align(a, 3)
     out["cfg1_150bp_2pct_cigar"] = entry(a, dt, st, parity_sample(a, range(0, 10000, 100), PEN, "oracle", orc, refcpu, a.options.max_error))
-    a.destroy()
+    release(a)
     # cfg 2: 1 000 000 x 150 bp, 5 %, score only
     a = make_aligner(wfagpu, 0xB2000002, 1000000, 150, 0.05, 0.05, PEN, cigar=False)
     dt, st = time_align(a, 2)
     out["cfg2_150bp_5pct_score_1M"] = entry(a, dt, st, parity_sample(a, range(0, 1000000, 10007), PEN, "oracle", orc, refcpu, a.options.max_error))
-    a.destroy()
+    release(a)
     # cfg 3: 100 000 x 1 kbp, 10 %, exact with CIGAR, -e 300 (about 5 % of the pairs exceed it: re-dispatched on the GPU)
     a = make_aligner(wfagpu, 0xB2000003, 100000, 1000, 0.10, 0.10, PEN, max_error=300, cigar=True)
     dt, st = time_align(a, 2)
     out["cfg3_1kbp_10pct_cigar_e300"] = entry(a, dt, st, parity_sample(a, range(0, 100000, 2503), PEN, "oracle", orc, refcpu, 300))
-    a.destroy()
+    release(a)
     # cfg 4 at full size: 100 000 x 10 kbp in ONE wfagpu_align call, error ~ U[1 %, 5 %], exact vs -B 25 -t 512
     a = make_aligner(wfagpu, 0xB2000004, 100000, 10000, 0.01, 0.05, PEN, max_error=MAX_ERROR, cigar=True)
     dt, st = time_align(a, 1)
@@ -365,7 +371,7 @@ def run_configs(wfagpu):
     out["cfg4_10kbp_1to5pct_cigar_band25_w512_100k"] = entry(
         a, dt, st, parity_sample(a, range(0, 100000, 12503), PEN, "oracle", orc, refcpu, MAX_ERROR, band=25, width=512),
         {"banded_recall": round(recall, 5), "note": "recall = pairs whose banded score equals the exact score"})
-    a.destroy()
+    release(a)
     # cfg 5: 50 kbp, 15 %, CIGAR, first budget (8000) below every score: every pair is re-dispatched on the GPU
     n5 = int(os.environ.get("WFAGPU_BENCH_CFG5_PAIRS", 256))
     a = make_aligner(wfagpu, 0xB2000005, n5, 50000, 0.15, 0.15, PEN, max_error=8000, cigar=True)
