@@ -233,6 +233,17 @@ long wfagpu_read_seq_file(wfagpu_aligner_t *aligner, const char *path, size_t ma
 long wfagpu_read_fasta_files(wfagpu_aligner_t *aligner, const char *query_path, const char *target_path,
                              size_t max_pairs);
 
+/* Incremental readers (streaming): every call appends the next `max_pairs` pairs (0 = all that are left) to the
+ * aligner's page-locked buffer; returns how many (0 at the end of the input, -1 on a format error). */
+typedef struct wfagpu_reader wfagpu_reader_t;
+wfagpu_reader_t *wfagpu_reader_open_seq(const char *path);
+wfagpu_reader_t *wfagpu_reader_open_fasta(const char *query_path, const char *target_path);
+long wfagpu_reader_next(wfagpu_reader_t *r, wfagpu_aligner_t *aligner, size_t max_pairs);
+long wfagpu_reader_total_bytes(const wfagpu_reader_t *r);
+void wfagpu_reader_close(wfagpu_reader_t *r);
+/* Forgets the pairs of an aligner but keeps its (page-locked) buffers, so that the next window of a stream reuses them. */
+void wfagpu_clear_sequences(wfagpu_aligner_t *aligner);
+
 /* `-c`: true iff `cigar` is a valid global alignment of (pattern, text) whose gap-affine cost is
  * `error` (replaces check_cigar_edit + check_affine_distance, utils/verification.c:27-146). */
 bool wfagpu_check_result(const char *pattern, size_t plen, const char *text, size_t tlen,

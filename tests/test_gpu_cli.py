@@ -66,3 +66,21 @@ def test_fasta_cigar_check_and_band(tmp_path, oracle):
     p, s = a.pair(3)
     r = oracle.align(p, s, 2, 3, 1, 3000, band=25, window=512)
     assert (-int(rows2[3][0]), rows2[3][1]) == (r["distance"], r["cigar"])
+
+
+def test_streaming_windows_give_the_same_output(tmp_path):
+    # -S N: the input is read / aligned / written N pairs at a time, the next window being read into page-locked
+    # memory while the GPU aligns the current one; same lines, same order
+    d = utest()
+    seq = tmp_path / "utest.seq"
+    with open(seq, "w") as f:
+        for p, t in zip(d["pattern"], d["text"]):
+            f.write(f">{p}\n<{t}\n")
+    whole, windows, capped = tmp_path / "whole.alg", tmp_path / "win.alg", tmp_path / "cap.alg"
+    run_cli(["-i", str(seq), "-o", str(whole), "-x", "-e", "400"])
+    pr = run_cli(["-i", str(seq), "-o", str(windows), "-x", "-e", "400", "-S", "64", "-c"])
+    assert "Streaming in windows of 64 pairs" in pr.stderr
+    assert "correct=305 Incorrect=0" in pr.stderr
+    assert open(whole).read() == open(windows).read()
+    run_cli(["-i", str(seq), "-o", str(capped), "-x", "-e", "400", "-S", "64", "-n", "100"])
+    assert open(capped).read().splitlines() == open(whole).read().splitlines()[:100]

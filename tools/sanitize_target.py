@@ -3,8 +3,9 @@
 
   compute-sanitizer --tool racecheck python tools/sanitize_target.py [family ...]
 
-families: warp (150 bp CIGAR, warp per pair), cta (1 kbp CIGAR: bound + CTA kernel + ring snapshots +
-traceback + CIGAR text), score (1 kbp score only), banded (-B 10, W=128, CIGAR), large
+families: warp (150 bp CIGAR, warp per pair), cta (1 kbp CIGAR: bound + four-diagonals-per-thread CTA kernel + ring
+snapshots + traceback + CIGAR text), quad_pairs (same with two scores per barrier), one_diag (the one-diagonal-per-
+thread kernel), workers (two host threads, one GPU), score (1 kbp score only), banded (-B 10, W=128, CIGAR), large
 (WFAGPU_FORCE_LARGE=1: rings in global memory), ascii (pairs with N: byte-compare kernels),
 redispatch (budget too small on purpose).  Every result is checked against the CPU oracle."""
 import os
@@ -23,6 +24,9 @@ FAMILIES = {
     "large":      (12, 600, 0.08, 200, True, -1, 0, {"WFAGPU_FORCE_LARGE": "1"}),
     "ascii":      (24, 400, 0.05, 100, True, -1, 0, {}),
     "redispatch": (32, 800, 0.10, 40, True, -1, 0, {}),
+    "quad_pairs": (40, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_QUAD_PAIRS": "1"}),      # two scores per barrier interval
+    "one_diag":   (24, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_NO_QUAD": "1"}),         # one diagonal per thread (the -c path)
+    "workers":    (96, 600, 0.06, 200, True, -1, 0, {"WFAGPU_DEVICES": "0,0"}),        # two workers, one GPU
 }
 
 
@@ -43,6 +47,8 @@ def run(name):
     if band > 0:
         a.options.band = band
         a.options.threads_per_block = width
+    if name == "workers":
+        a.set_batch_size(24)
     a.align()
     orc = Oracle()
     bad = 0

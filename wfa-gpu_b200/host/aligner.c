@@ -243,6 +243,14 @@ bool wfagpu_align(wfagpu_aligner_t *aligner)
     return wfagpu_last_launch_ok();
 }
 
+/* Extension: forget the pairs, keep the buffers (streaming: the next window is read into the same pinned memory). */
+void wfagpu_clear_sequences(wfagpu_aligner_t *aligner)
+{
+    if (!aligner) return;
+    aligner->last_sequence_pair_idx = -1;
+    aligner->num_sequence_pairs = 0;
+}
+
 /* Extension: forget the CIGAR text of a previous wfagpu_align so that the same
  * aligner can be aligned again (the reference appends to the old text). */
 void wfagpu_reset_results(wfagpu_aligner_t *aligner)

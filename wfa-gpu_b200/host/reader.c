@@ -29,42 +29,21 @@ static size_t chomp(char *line, ssize_t n)
     return (size_t)n;
 }
 
-long wfagpu_read_seq_file(wfagpu_aligner_t *aligner, const char *path, size_t max_pairs)
-{
-    FILE *fp = fopen(path, "r");
-    if (!fp) { fprintf(stderr, "[!] ERROR: Could not open %s\n", path); return -1; }
-    if (max_pairs == 0) {
-        /* one page-locked allocation for the whole file instead of geometric growth */
-        const long fsz = file_size(fp);
-        if (fsz > 0) wfagpu_reserve(aligner, (size_t)fsz + (size_t)fsz / 16 + 4096, 0);
-    }
-    char *line = NULL, *pattern = NULL;
-    size_t cap = 0, lineno = 0;
-    ssize_t n;
-    long pairs = 0;
-    bool ok = true;
-    while (ok && (max_pairs == 0 || (size_t)pairs < max_pairs) && (n = getline(&line, &cap, fp)) != -1) {
-        ++lineno;
-        const size_t len = chomp(line, n);
-        if (len == 0) continue;
-        if (!pattern) {
-            if (line[0] != '>') { fprintf(stderr, "[!] ERROR: Invalid file format. Could not read pattern in line %zu\n", lineno); ok = false; break; }
-            pattern = strdup(line + 1);
-        } else {
-            if (line[0] != '<') { fprintf(stderr, "[!] ERROR: Invalid file format. Could not read text in line %zu\n", lineno); ok = false; break; }
-            ok = wfagpu_add_sequences(aligner, pattern, line + 1);
-            free(pattern);
-            pattern = NULL;
-            ++pairs;
-        }
-    }
-    free(pattern);
-    free(line);
-    fclose(fp);
-    return ok ? pairs : -1;
-}
-
+/* ---- incremental readers: the next `max_pairs` pairs of a .seq file or of a FASTA pair go straight into the
+ * aligner's page-locked buffer.  The CLI streams with them (window w + 1 is read while the GPU aligns window w)
+ * instead of "load everything, then align" (README.md:120-121 of the reference). ---- */
 typedef struct { FILE *fp; char *line; size_t cap; bool eof; bool pending_header; } fasta_t;
+
+struct wfagpu_reader {
+    bool fasta;
+    FILE *fp;              /* .seq */
+    char *line;
+    size_t cap, lineno;
+    fasta_t q, t;          /* FASTA */
+    char *qs, *ts;
+    size_t qc, tc;
+    long total_bytes;      /* size of the input (both files), for one up-front reservation */
+};
 
 static bool is_header(const char *s) { while (*s == ' ') ++s; return *s == '>'; }
 
@@ -94,36 +73,105 @@ static bool fasta_next(fasta_t *f, char **seq, size_t *seq_cap)
     return any;
 }
 
-long wfagpu_read_fasta_files(wfagpu_aligner_t *aligner, const char *query_path, const char *target_path, size_t max_pairs)
+wfagpu_reader_t *wfagpu_reader_open_seq(const char *path)
 {
-    fasta_t q = {0}, t = {0};
-    q.fp = fopen(query_path, "r");
-    t.fp = fopen(target_path, "r");
-    if (!q.fp || !t.fp) {
-        fprintf(stderr, "[!] ERROR: Could not open %s\n", !q.fp ? query_path : target_path);
-        if (q.fp) fclose(q.fp);
-        if (t.fp) fclose(t.fp);
-        return -1;
+    FILE *fp = fopen(path, "r");
+    if (!fp) { fprintf(stderr, "[!] ERROR: Could not open %s\n", path); return NULL; }
+    wfagpu_reader_t *r = (wfagpu_reader_t *)calloc(1, sizeof(*r));
+    if (!r) { fclose(fp); return NULL; }
+    r->fp = fp;
+    r->total_bytes = file_size(fp);
+    return r;
+}
+
+wfagpu_reader_t *wfagpu_reader_open_fasta(const char *query_path, const char *target_path)
+{
+    FILE *q = fopen(query_path, "r"), *t = fopen(target_path, "r");
+    if (!q || !t) {
+        fprintf(stderr, "[!] ERROR: Could not open %s\n", !q ? query_path : target_path);
+        if (q) fclose(q);
+        if (t) fclose(t);
+        return NULL;
     }
-    if (max_pairs == 0) {
-        const long a = file_size(q.fp), b = file_size(t.fp);
-        if (a > 0 && b > 0) wfagpu_reserve(aligner, (size_t)(a + b) + (size_t)(a + b) / 16 + 4096, 0);
-    }
-    char *qs = NULL, *ts = NULL;
-    size_t qc = 0, tc = 0;
+    wfagpu_reader_t *r = (wfagpu_reader_t *)calloc(1, sizeof(*r));
+    if (!r) { fclose(q); fclose(t); return NULL; }
+    r->fasta = true;
+    r->q.fp = q;
+    r->t.fp = t;
+    const long a = file_size(q), b = file_size(t);
+    r->total_bytes = (a > 0 && b > 0) ? a + b : -1;
+    return r;
+}
+
+long wfagpu_reader_total_bytes(const wfagpu_reader_t *r) { return r ? r->total_bytes : -1; }
+
+long wfagpu_reader_next(wfagpu_reader_t *r, wfagpu_aligner_t *aligner, size_t max_pairs)
+{
+    if (!r || !aligner) return -1;
     long pairs = 0;
     bool ok = true;
-    while (ok && (max_pairs == 0 || (size_t)pairs < max_pairs)) {
-        const bool hq = fasta_next(&q, &qs, &qc);
-        const bool ht = fasta_next(&t, &ts, &tc);
-        if (!hq || !ht) break;
-        ok = wfagpu_add_sequences(aligner, qs, ts);
-        ++pairs;
+    if (r->fasta) {
+        while (ok && (max_pairs == 0 || (size_t)pairs < max_pairs)) {
+            const bool hq = fasta_next(&r->q, &r->qs, &r->qc);
+            const bool ht = fasta_next(&r->t, &r->ts, &r->tc);
+            if (!hq || !ht) break;
+            ok = wfagpu_add_sequences(aligner, r->qs, r->ts);
+            ++pairs;
+        }
+        return ok ? pairs : -1;
     }
-    free(qs); free(ts); free(q.line); free(t.line);
-    fclose(q.fp); fclose(t.fp);
-    if (pairs == 0 && ok) { fprintf(stderr, "[!] ERROR: Empty FASTA file.\n"); return -1; }
+    char *pattern = NULL;
+    ssize_t n;
+    while (ok && (max_pairs == 0 || (size_t)pairs < max_pairs) && (n = getline(&r->line, &r->cap, r->fp)) != -1) {
+        ++r->lineno;
+        const size_t len = chomp(r->line, n);
+        if (len == 0) continue;
+        if (!pattern) {
+            if (r->line[0] != '>') { fprintf(stderr, "[!] ERROR: Invalid file format. Could not read pattern in line %zu\n", r->lineno); ok = false; break; }
+            pattern = strdup(r->line + 1);
+        } else {
+            if (r->line[0] != '<') { fprintf(stderr, "[!] ERROR: Invalid file format. Could not read text in line %zu\n", r->lineno); ok = false; break; }
+            ok = wfagpu_add_sequences(aligner, pattern, r->line + 1);
+            free(pattern);
+            pattern = NULL;
+            ++pairs;
+        }
+    }
+    free(pattern);
     return ok ? pairs : -1;
+}
+
+void wfagpu_reader_close(wfagpu_reader_t *r)
+{
+    if (!r) return;
+    if (r->fp) fclose(r->fp);
+    if (r->q.fp) fclose(r->q.fp);
+    if (r->t.fp) fclose(r->t.fp);
+    free(r->line); free(r->q.line); free(r->t.line); free(r->qs); free(r->ts);
+    free(r);
+}
+
+static long read_all(wfagpu_reader_t *r, wfagpu_aligner_t *aligner, size_t max_pairs)
+{
+    if (!r) return -1;
+    if (max_pairs == 0 && r->total_bytes > 0)
+        /* one page-locked allocation for the whole input instead of geometric growth */
+        wfagpu_reserve(aligner, (size_t)r->total_bytes + (size_t)r->total_bytes / 16 + 4096, 0);
+    const long pairs = wfagpu_reader_next(r, aligner, max_pairs);
+    wfagpu_reader_close(r);
+    return pairs;
+}
+
+long wfagpu_read_seq_file(wfagpu_aligner_t *aligner, const char *path, size_t max_pairs)
+{
+    return read_all(wfagpu_reader_open_seq(path), aligner, max_pairs);
+}
+
+long wfagpu_read_fasta_files(wfagpu_aligner_t *aligner, const char *query_path, const char *target_path, size_t max_pairs)
+{
+    const long pairs = read_all(wfagpu_reader_open_fasta(query_path, target_path), aligner, max_pairs);
+    if (pairs == 0) { fprintf(stderr, "[!] ERROR: Empty FASTA file.\n"); return -1; }
+    return pairs;
 }
 
 /* -c: validates a result without any CPU aligner (replaces check_cigar_edit +
