@@ -439,19 +439,32 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
         c->groups_per_cta = 1;
         c->stages = 1;
         c->n_cap = n_want;
+        /* packed pairs: four diagonals per thread with 128-bit loads (wfa_quadg_kernel): rows 16-byte aligned */
+        c->quad = !ascii && !d->no_quad;
+        ck = c->quad;
         c->row_stride = rs(n_want);
-        c->center = n_want + 2 * G + 1;
-        c->smem = exact_smem_bytes(A, E1, 0, seq_words, 1, 1);     /* sequences + control only */
+        c->center = c->quad ? ctr(n_want) : n_want + 2 * G + 1;
+        c->smem = exact_smem_bytes(A, E1, 0, seq_words, 1, 1, c->quad);     /* sequences + control (+ schedule records) only */
         if (!ascii && c->smem > smem_max) {
             fprintf(stderr, "[wfagpu] sequences of %u bases do not fit in shared memory; not supported yet\n", max_len);
             return -2;
         }
-        /* wide wavefronts (50 kbp / 15 %: ~10 k diagonals per score) keep 1024 threads busy: 581 vs 416
-         * pairs/s against 512 threads on B200 */
-        c->group_threads = d->force_threads ? d->force_threads : (n_want >= 2048 ? 1024 : 512);
-        int occ = large_max_ctas_per_sm(c->group_threads, c->smem, ascii, bt);
-        if (occ < 1) return -1;
-        occ = std::min(occ, d->force_ctas_per_sm ? d->force_ctas_per_sm : 2);
+        int occ;
+        if (c->quad) {
+            /* one CTA per SM -- 148 x 0.7 MB of rings stay resident in the 126 MB L2 (two per SM: 681 instead of 902 pairs/s
+             * at 50 kbp / 15 %); measured on B200, 592 pairs: 512 threads 1030, 768 1077, 1024 (64 registers) 1098 pairs/s */
+            c->group_threads = d->force_threads ? d->force_threads : (n_want >= 2048 ? 1024 : (n_want >= 512 ? 512 : 256));
+            occ = quadg_max_ctas_per_sm(c->group_threads, c->smem, bt);
+            if (occ < 1) return -1;
+            occ = std::min(occ, d->force_ctas_per_sm ? d->force_ctas_per_sm : 1);
+        } else {
+            /* wide wavefronts (50 kbp / 15 %: ~10 k diagonals per score) keep 1024 threads busy: 581 vs 416
+             * pairs/s against 512 threads on B200 */
+            c->group_threads = d->force_threads ? d->force_threads : (n_want >= 2048 ? 1024 : 512);
+            occ = large_max_ctas_per_sm(c->group_threads, c->smem, ascii, bt);
+            if (occ < 1) return -1;
+            occ = std::min(occ, d->force_ctas_per_sm ? d->force_ctas_per_sm : 2);
+        }
         c->ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ * d->prop.multiProcessorCount, n_items));
         return 0;
     }
@@ -891,7 +904,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     if (env_int("WFAGPU_VERBOSE", 0))
         fprintf(stderr, "[wfagpu] pass: items=%zu max_steps=%d n_cap=%d d_end=%d group=%d x%d ctas=%d stages=%d smem=%zu ascii=%d band=%d tier=%s period=%d arena=%.1f MB\n",
                 n_items, max_steps, c.n_cap, d_end, c.group_threads, c.groups_per_cta, c.ctas, c.stages, c.smem,
-                (int)ascii, plan.band > 0 ? win : 0, c.global_ring ? "global-int32" : (c.quad ? (c.quad_pairs ? (c.ckpt ? "smem-int16x4x2+ckpt" : "smem-int16x4x2") : (c.ckpt ? "smem-int16x4+ckpt" : "smem-int16x4")) : (c.ckpt ? "smem-int16+ckpt" : "smem-int16")), period, arenas * arena_units * 16.0 / 1e6);
+                (int)ascii, plan.band > 0 ? win : 0, c.global_ring ? (c.quad ? "global-int32x4" : "global-int32") : (c.quad ? (c.quad_pairs ? (c.ckpt ? "smem-int16x4x2+ckpt" : "smem-int16x4x2") : (c.ckpt ? "smem-int16x4+ckpt" : "smem-int16x4")) : (c.ckpt ? "smem-int16+ckpt" : "smem-int16")), period, arenas * arena_units * 16.0 / 1e6);
     int tb_ctas = 0;
     constexpr int kTbWarps = 8;
     if (c.ckpt) {
@@ -924,6 +937,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         const bool time_it = first_pass && items_per_launch >= n_items && s.ev[6] && s.ev[7];
         if (time_it) CK(cudaEventRecord(s.ev[6], s.stream));
         cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
+                      : (c.quad && c.global_ring) ? launch_quadg(kp, c.group_threads, (int)std::min<size_t>(c.ctas, cnt), c.smem, s.stream)
                       : c.quad ? launch_quad(kp, c.group_threads, (int)std::min<size_t>(c.ctas, cnt), c.smem, s.stream)
                                : launch_exact(kp, c.group_threads, c.groups_per_cta, (int)std::min<size_t>(c.ctas, cnt), c.smem, ascii, s.stream);
         if (e != cudaSuccess) {

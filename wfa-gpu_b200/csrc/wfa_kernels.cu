@@ -848,9 +848,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
     return v;
 }
 
-__device__ __noinline__ int extend_packed_general(uint32_t Pa, uint32_t Ta, int plen, int tlen, int k, int off)
+__device__ __noinline__ int extend_packed_general(uint32_t Pa, uint32_t Ta, int plen, int tlen, int k, int off, int null_v)
 {
-    return extend_packed(Pa, Ta, plen, tlen, k, off, kOffNull);
+    return extend_packed(Pa, Ta, plen, tlen, k, off, null_v);
 }
 
 /* The common case of an extend, branch-free so that the four cells of a quad overlap: returns the
@@ -898,13 +898,12 @@ __device__ __forceinline__ uint32_t in2(int k, int lo, int hi)
 }
 __device__ __forceinline__ uint32_t sel2(uint32_t v, uint32_t mask) { return (v & mask) | (kNull2 & ~mask); }
 
-/* extend the four M cells (M01 | M23) of the quad that starts at diagonal kq */
-__device__ __forceinline__ void extend_quad(uint32_t Pa, uint32_t Ta, int plen, int tlen, int kq, int tl8,
-                                            uint32_t &M01, uint32_t &M23)
+/* extend the four M cells m0 .. m3 of the quad that starts at diagonal kq (null_v: what a cell outside the
+ * sequences becomes; the probes treat every negative offset as NULL) */
+__device__ __forceinline__ void extend_cells(uint32_t Pa, uint32_t Ta, int plen, int tlen, int kq, int tl8,
+                                             int &m0, int &m1, int &m2, int &m3, const int null_v)
 {
     const int c8 = kq + plen - 8;
-    int m0 = (int)(short)(M01 & 0xffffu), m1 = (int)M01 >> 16;
-    int m2 = (int)(short)(M23 & 0xffffu), m3 = (int)M23 >> 16;
     const uint32_t f0 = extend_probe(Pa, Ta, kq, m0, __viaddmin_s32_relu(c8, 0, tl8));
     const uint32_t f1 = extend_probe(Pa, Ta, kq + 1, m1, __viaddmin_s32_relu(c8, 1, tl8));
     const uint32_t f2 = extend_probe(Pa, Ta, kq + 2, m2, __viaddmin_s32_relu(c8, 2, tl8));
@@ -918,11 +917,20 @@ __device__ __forceinline__ void extend_quad(uint32_t Pa, uint32_t Ta, int plen, 
     m2 = add_run(m2, f2);
     m3 = add_run(m3, f3);
     if (min(min(z0, z1), min(z2, z3)) < 0x4000u) {
-        if (z0 < 0x4000u) m0 = extend_packed_general(Pa, Ta, plen, tlen, kq, m0);
-        if (z1 < 0x4000u) m1 = extend_packed_general(Pa, Ta, plen, tlen, kq + 1, m1);
-        if (z2 < 0x4000u) m2 = extend_packed_general(Pa, Ta, plen, tlen, kq + 2, m2);
-        if (z3 < 0x4000u) m3 = extend_packed_general(Pa, Ta, plen, tlen, kq + 3, m3);
+        if (z0 < 0x4000u) m0 = extend_packed_general(Pa, Ta, plen, tlen, kq, m0, null_v);
+        if (z1 < 0x4000u) m1 = extend_packed_general(Pa, Ta, plen, tlen, kq + 1, m1, null_v);
+        if (z2 < 0x4000u) m2 = extend_packed_general(Pa, Ta, plen, tlen, kq + 2, m2, null_v);
+        if (z3 < 0x4000u) m3 = extend_packed_general(Pa, Ta, plen, tlen, kq + 3, m3, null_v);
     }
+}
+
+/* the same on two packed int16 pairs (M01 | M23) */
+__device__ __forceinline__ void extend_quad(uint32_t Pa, uint32_t Ta, int plen, int tlen, int kq, int tl8,
+                                            uint32_t &M01, uint32_t &M23)
+{
+    int m0 = (int)(short)(M01 & 0xffffu), m1 = (int)M01 >> 16;
+    int m2 = (int)(short)(M23 & 0xffffu), m3 = (int)M23 >> 16;
+    extend_cells(Pa, Ta, plen, tlen, kq, tl8, m0, m1, m2, m3, kOffNull);
     M01 = __byte_perm((uint32_t)m0, (uint32_t)m1, 0x5410);
     M23 = __byte_perm((uint32_t)m2, (uint32_t)m3, 0x5410);
 }
@@ -1311,6 +1319,293 @@ __global__ void __launch_bounds__(512, 1) wfa_quad_kernel(const __grid_constant_
     }
 }
 
+
+/* ======================================================================== */
+/*   large tier: rings in global memory (L2), int32, four diagonals/thread  */
+/* ======================================================================== */
+/*
+ * For wavefronts wider than one CTA's shared memory and for sequences of 32768 bases and more (BASELINE
+ * config 5: 50 kbp / 15 % has windows of ~20 000 diagonals, 720 KB of rings per pair).  Same recurrence,
+ * pruning windows, schedule records and extend as wfa_quad_kernel; the rings are int32 rows in global memory that
+ * stay resident in L2 (one CTA per SM: 148 x 0.7 MB), read with 128-bit loads (4 x LDG.128 + 4 x LDG.32 per four
+ * cells instead of 20 scalar loads with 64-bit address arithmetic), written with 3 x STG.128; the backtrace is one
+ * decision byte per cell (bit0 I extends, bit1 D extends, bits 3:2 the winner of M), walked by the CTA's leader.
+ * Only the packed sequences and the schedule records live in shared memory.
+ */
+__device__ __forceinline__ int selnull(int v, bool in, int null_v) { return in ? v : null_v; }
+
+template <bool BT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) wfa_quadg_kernel(const __grid_constant__ KernelParams p)
+{
+    constexpr int NULLV = RingG32::kNull;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, gsz = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, last_warp = (gsz >> 5) - 1;
+
+    /* shared memory: [sequences, one stage][ctl][schedule records] */
+    const uint32_t seq_bytes = (uint32_t)p.seq_words * 4u;
+    const uint32_t seq_sa = smem_u32(smem_raw);
+    GroupCtl *ctl = reinterpret_cast<GroupCtl *>(smem_raw + 2u * seq_bytes);
+    const uint32_t sched_sa = seq_sa + 2u * seq_bytes + (uint32_t)sizeof(GroupCtl);
+
+    const int x = p.x, e = p.e, A = p.A, E1 = p.E1, GW = p.G;
+    const int oe = p.o + p.e;
+    const uint32_t RS = (uint32_t)p.row_stride;                          /* int32 elements per row, multiple of 4 */
+    int32_t *const ring = p.gring + (size_t)blockIdx.x * p.gring_elems;     /* 16-byte aligned */
+    const uint32_t M0 = (uint32_t)p.center, I0 = M0 + (uint32_t)A * RS, D0 = I0 + (uint32_t)E1 * RS;   /* diagonal 0 of row 0 */
+    const int rows = A + 2 * E1;
+    uint4 *const arena = p.arena + (size_t)blockIdx.x * p.arena_units;
+    uint32_t *const scratch = p.ops_scratch + (size_t)blockIdx.x * p.ops_scratch_words;
+
+    auto issue_load = [&](uint32_t idx) {
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const uint32_t pw = ((((pr.plen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        const uint32_t tw = ((((pr.tlen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        fence_proxy_async();
+        mbar_expect_tx(&ctl->bar[0], (pw + tw) * 4u);
+        tma_load_1d(smem_raw, p.packed + pr.p_word, pw * 4u, &ctl->bar[0]);
+        tma_load_1d(smem_raw + seq_bytes, p.packed + pr.t_word, tw * 4u, &ctl->bar[0]);
+    };
+    auto pop = [&]() -> uint32_t {
+        const uint32_t pos = atomicAdd(p.queue, 1u);
+        return pos < p.n_items ? p.order[pos] : kInvalidIdx;
+    };
+    if (tid == 0) {
+        mbar_init(&ctl->bar[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t first = pop();
+        ctl->idx[0] = first;
+        if (first != kInvalidIdx) issue_load(first);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    while (true) {
+        const uint32_t idx = ctl->idx[0];
+        if (idx == kInvalidIdx) break;
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const int plen = (int)pr.plen, tlen = (int)pr.tlen;
+        const int kt = tlen - plen;
+        const uint32_t Pa = seq_sa, Ta = seq_sa + seq_bytes;
+        const bool skip = (pr.flags & WFAGPU_PAIR_HAS_N) != 0;
+
+        /* ring prologue: NULL over [-2G - 4, 2G + 4] on every row */
+        {
+            const int span = 4 * GW + 9;
+            const int total = rows * span;
+            for (int i = tid; i < total; i += gsz) {
+                const int r = i / span;
+                ring[M0 + (uint32_t)r * RS + (uint32_t)(i - r * span - 2 * GW - 4)] = NULLV;
+            }
+        }
+        mbar_wait(&ctl->bar[0], phase);
+        phase ^= 1u;
+        __syncthreads();
+
+        int dist = 0;
+        bool finished = false;
+        if (!skip) {
+            const int Dmax = p.bound ? min(p.d_end - 1, p.bound[idx]) : p.d_end - 1;
+            auto fill_sched = [&](int dbase, int buf) {
+                const int d = dbase + tid;
+                StepRec r;
+                r.lo = 0; r.hi = -1; r.flags = kRecStop; r.n = 0; r.ck_j = 0;
+                r.aMc = r.aMx = r.aMo = r.aIc = r.aIe = r.aDc = r.aDe = 0;
+                if (d <= Dmax) {
+                    const wfagpu_step_t st = p.steps[d];
+                    int lo, hi;
+                    const bool live = prune_window((int)st.n, kt, (Dmax - d) / e, p.n_cap, lo, hi);
+                    const bool stop = live && (lo < -p.n_cap || hi > p.n_cap);
+                    const bool work = live && st.kind != WFAGPU_STEP_NULL;
+                    r.lo = lo; r.hi = hi; r.n = (int)st.n;
+                    r.flags = (uint32_t)st.kind | (live ? kRecLive : 0u) | (stop ? kRecStop : 0u) |
+                              ((work && kt >= lo && kt <= hi) ? kRecTarget : 0u);
+                    r.ck_j = st.row_off;                                   /* decision row of this score */
+                    const int dm = d % A, de1 = d % E1;
+                    int sx = dm - x % A; if (sx < 0) sx += A;
+                    int so = dm - oe % A; if (so < 0) so += A;
+                    int se = de1 - e % E1; if (se < 0) se += E1;
+                    r.aMc = M0 + (uint32_t)dm * RS; r.aMx = M0 + (uint32_t)sx * RS; r.aMo = M0 + (uint32_t)so * RS;
+                    r.aIc = I0 + (uint32_t)de1 * RS; r.aIe = I0 + (uint32_t)se * RS;
+                    r.aDc = D0 + (uint32_t)de1 * RS; r.aDe = D0 + (uint32_t)se * RS;
+                }
+                const uint32_t a = sched_sa + (uint32_t)(buf * kSchedBlock + tid) * (uint32_t)sizeof(StepRec);
+                sts_v4(a, make_uint4((uint32_t)r.lo, (uint32_t)r.hi, r.flags, (uint32_t)r.n));
+                sts_v4(a + 16u, make_uint4(r.aMc, r.aMx, r.aMo, r.aIc));
+                sts_v4(a + 32u, make_uint4(r.aIe, r.aDc, r.aDe, r.ck_j));
+            };
+            if (tid == 0) ring[M0] = extend_packed(Pa, Ta, plen, tlen, 0, 0, NULLV);
+            if (tid < kSchedBlock) fill_sched(1, 0);
+            __syncthreads();
+            if (kt == 0 && ring[M0] == tlen) {
+                finished = true;
+            } else {
+                const int tl8 = tlen - 8;
+                unsigned long long n_cells = 0;
+                int last_blk = -1;
+                for (int d = 1; d <= Dmax; ++d) {
+                    const int blk = (d - 1) / kSchedBlock;
+                    if (blk != last_blk) {
+                        last_blk = blk;
+                        if (tid < kSchedBlock) fill_sched((blk + 1) * kSchedBlock + 1, (blk + 1) & 1);
+                    }
+                    const uint32_t ra = sched_sa + (uint32_t)((blk & 1) * kSchedBlock + ((d - 1) & (kSchedBlock - 1))) * (uint32_t)sizeof(StepRec);
+                    const uint4 r0 = lds_v4(ra), r1 = lds_v4(ra + 16u), r2 = lds_v4(ra + 32u);
+                    if (r0.z & kRecStop) break;
+                    const int lo = (int)r0.x, hi = (int)r0.y, n = (int)r0.w;
+                    const int kind = (int)(r0.z & 3u);
+                    const bool live = (r0.z & kRecLive) != 0;
+                    int32_t *const rMc = ring + r1.x, *const rIc = ring + r1.w, *const rDc = ring + r2.y;
+                    const int32_t *const rMx = ring + r1.y, *const rMo = ring + r1.z, *const rIe = ring + r2.x, *const rDe = ring + r2.z;
+                    if (p.cells && live && kind != WFAGPU_STEP_NULL) n_cells += (unsigned)(hi - lo + 1);
+
+                    if (kind == WFAGPU_STEP_MDI && live) {
+                        const int kq0 = lo & ~3, kend = hi | 3;
+                        if (warp == last_warp) {
+                            for (int g = lane; g < 2 * GW; g += 32) {
+                                const int k = (g < GW) ? (kq0 - 1 - g) : (kend + 1 + (g - GW));
+                                rMc[k] = NULLV; rIc[k] = NULLV; rDc[k] = NULLV;
+                            }
+                        }
+                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + r2.w) + n;      /* decision row, indexed by k */
+                        for (int kq = kq0 + 4 * tid; kq <= hi; kq += 4 * gsz) {
+                            const int4 mo = *reinterpret_cast<const int4 *>(rMo + kq);
+                            const int ml = rMo[kq - 1], mr = rMo[kq + 4];
+                            const int4 ie = *reinterpret_cast<const int4 *>(rIe + kq);
+                            const int il = rIe[kq - 1];
+                            const int4 de = *reinterpret_cast<const int4 *>(rDe + kq);
+                            const int dr = rDe[kq + 4];
+                            const int4 mx = *reinterpret_cast<const int4 *>(rMx + kq);
+                            /* offsets by plain max; the tie-breaks only decide the backtrace bits: I / D: extend beats open
+                             * on equal offsets; M: D beats X beats I */
+                            int i0 = max(ml, il) + 1, i1 = max(mo.x, ie.x) + 1, i2 = max(mo.y, ie.y) + 1, i3 = max(mo.z, ie.z) + 1;
+                            int d0 = max(mo.y, de.y), d1 = max(mo.z, de.z), d2 = max(mo.w, de.w), d3 = max(mr, dr);
+                            const int x0 = mx.x + 1, x1 = mx.y + 1, x2 = mx.z + 1, x3 = mx.w + 1;
+                            int m0 = max(max(x0, d0), i0), m1 = max(max(x1, d1), i1), m2 = max(max(x2, d2), i2), m3 = max(max(x3, d3), i3);
+                            if (BT) {
+                                const uint32_t c0 = (il >= ml ? 1u : 0u) | (de.y >= mo.y ? 2u : 0u) | ((d0 >= x0 || i0 > x0) ? 4u : 0u) | ((d0 >= i0 || x0 >= i0) ? 8u : 0u);
+                                const uint32_t c1 = (ie.x >= mo.x ? 1u : 0u) | (de.z >= mo.z ? 2u : 0u) | ((d1 >= x1 || i1 > x1) ? 4u : 0u) | ((d1 >= i1 || x1 >= i1) ? 8u : 0u);
+                                const uint32_t c2 = (ie.y >= mo.y ? 1u : 0u) | (de.w >= mo.w ? 2u : 0u) | ((d2 >= x2 || i2 > x2) ? 4u : 0u) | ((d2 >= i2 || x2 >= i2) ? 8u : 0u);
+                                const uint32_t c3 = (ie.z >= mo.z ? 1u : 0u) | (dr >= mr ? 2u : 0u) | ((d3 >= x3 || i3 > x3) ? 4u : 0u) | ((d3 >= i3 || x3 >= i3) ? 8u : 0u);
+                                /* cells outside the window keep their byte unwritten: the traceback never visits them */
+                                if (kq >= lo) rowb[kq] = (uint8_t)c0;
+                                if (kq + 1 >= lo && kq + 1 <= hi) rowb[kq + 1] = (uint8_t)c1;
+                                if (kq + 2 >= lo && kq + 2 <= hi) rowb[kq + 2] = (uint8_t)c2;
+                                if (kq + 3 <= hi) rowb[kq + 3] = (uint8_t)c3;
+                            }
+                            if (kq < lo || kq + 3 > hi) {
+                                const bool in0 = kq >= lo, in1 = kq + 1 >= lo && kq + 1 <= hi, in2 = kq + 2 >= lo && kq + 2 <= hi, in3 = kq + 3 <= hi;
+                                i0 = selnull(i0, in0, NULLV); d0 = selnull(d0, in0, NULLV); m0 = selnull(m0, in0, NULLV);
+                                i1 = selnull(i1, in1, NULLV); d1 = selnull(d1, in1, NULLV); m1 = selnull(m1, in1, NULLV);
+                                i2 = selnull(i2, in2, NULLV); d2 = selnull(d2, in2, NULLV); m2 = selnull(m2, in2, NULLV);
+                                i3 = selnull(i3, in3, NULLV); d3 = selnull(d3, in3, NULLV); m3 = selnull(m3, in3, NULLV);
+                            }
+                            *reinterpret_cast<int4 *>(rIc + kq) = make_int4(i0, i1, i2, i3);
+                            *reinterpret_cast<int4 *>(rDc + kq) = make_int4(d0, d1, d2, d3);
+                            extend_cells(Pa, Ta, plen, tlen, kq, tl8, m0, m1, m2, m3, NULLV);
+                            *reinterpret_cast<int4 *>(rMc + kq) = make_int4(m0, m1, m2, m3);
+                        }
+                    } else if (kind == WFAGPU_STEP_NULL || !live) {
+                        for (int k = lo - GW - 4 + tid; k <= hi + GW + 4; k += gsz) { rMc[k] = NULLV; rIc[k] = NULLV; rDc[k] = NULLV; }
+                        __syncthreads();
+                        continue;
+                    } else {
+                        for (int k = lo - GW - 4 + tid; k <= hi + GW + 4; k += gsz) {
+                            rIc[k] = NULLV; rDc[k] = NULLV;
+                            int m = NULLV;
+                            if (k >= lo && k <= hi) {
+                                m = rMx[k] + 1;
+                                if (m >= 0) m = extend_packed(Pa, Ta, plen, tlen, k, m, NULLV);
+                            }
+                            rMc[k] = m;
+                        }
+                    }
+                    __syncthreads();
+                    if ((r0.z & kRecTarget) != 0 && rMc[kt] == tlen) { finished = true; dist = d; break; }
+                }
+                if (p.cells && tid == 0) atomicAdd(p.cells, n_cells);
+            }
+        }
+
+        /* ---- traceback over the decision bytes -> 2-bit ops, newest first (leader) ---- */
+        uint32_t n_ops = 0;
+        if (tid == 0) {
+            uint32_t ops_off = 0;
+            if (BT && finished && dist > 0) {
+                int cd = dist, ck = kt, comp = 0;
+                uint32_t word = 0;
+                while (!(comp == 0 && cd == 0)) {
+                    const wfagpu_step_t st = p.steps[cd];
+                    uint32_t op;
+                    if (comp == 0) {
+                        op = OP_SUB;
+                        if (st.kind == WFAGPU_STEP_M) {
+                            cd -= x;
+                        } else {
+                            const int ii = ck + (int)st.n;
+                            if (ii < 0 || ii > 2 * (int)st.n) { n_ops = 0; finished = false; break; }
+                            const uint32_t dec = reinterpret_cast<const uint8_t *>(arena + st.row_off)[ii];
+                            const int mop = (int)(dec >> 2) & 3;
+                            if (mop == OP_SUB) cd -= x;
+                            else if (mop == OP_INS) comp = 1;
+                            else comp = 2;
+                        }
+                    } else {
+                        const int ii = ck + (int)st.n;
+                        if (ii < 0 || ii > 2 * (int)st.n || st.kind != WFAGPU_STEP_MDI) { n_ops = 0; finished = false; break; }
+                        const uint32_t dec = reinterpret_cast<const uint8_t *>(arena + st.row_off)[ii];
+                        if (comp == 1) {
+                            op = OP_INS;
+                            ck -= 1;
+                            if (dec & 1u) cd -= e; else { cd -= oe; comp = 0; }
+                        } else {
+                            op = OP_DEL;
+                            ck += 1;
+                            if (dec & 2u) cd -= e; else { cd -= oe; comp = 0; }
+                        }
+                    }
+                    word |= op << (2 * (n_ops & 15u));
+                    ++n_ops;
+                    if ((n_ops & 15u) == 0) { scratch[(n_ops >> 4) - 1] = word; word = 0; }
+                    if (cd < 0 || (n_ops >> 4) >= p.ops_scratch_words) { n_ops = 0; finished = false; break; }
+                }
+                if (n_ops & 15u) scratch[n_ops >> 4] = word;
+                const uint32_t nw = (n_ops + 15u) >> 4;
+                ops_off = atomicAdd(p.ops_pool_head, nw);
+                if (ops_off + nw > p.ops_pool_words) { n_ops = 0; finished = false; }
+            }
+            ctl->n_ops = n_ops;
+            ctl->ops_off = ops_off;
+            wfagpu_pair_out_t r;
+            r.distance = finished ? dist : 0;
+            r.ops_off = ops_off;
+            r.n_ops = n_ops;
+            if (skip) {
+                r.status = WFAGPU_ST_NEEDS_ASCII;
+                p.ascii_list[atomicAdd(p.ascii_count, 1u)] = idx;
+            } else if (finished) {
+                r.status = WFAGPU_ST_FINISHED;
+            } else {
+                r.status = WFAGPU_ST_OVERBUDGET;
+                p.retry_list[atomicAdd(p.retry_count, 1u)] = idx;
+            }
+            p.out[idx] = r;
+        }
+        __syncthreads();
+        if (BT) {
+            const uint32_t nw = (ctl->n_ops + 15u) >> 4;
+            const uint32_t off = ctl->ops_off;
+            for (uint32_t i = tid; i < nw; i += gsz) p.ops_pool[off + i] = scratch[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t nxt = pop();
+            ctl->idx[0] = nxt;
+            if (nxt != kInvalidIdx) issue_load(nxt);
+        }
+        __syncthreads();
+    }
+}
 
 /* ======================================================================== */
 /*              score upper bound (warp per pair, 32 diagonals)             */
@@ -2288,6 +2583,41 @@ int quad_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
     }
     return n;
+}
+
+template <bool BT, int MAXT>
+static cudaError_t launch_quadg_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
+{
+    auto kfn = wfa_quadg_kernel<BT, MAXT>;
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kfn<<<ctas, threads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <bool BT, int MAXT>
+static int occupancy_quadg_one(int threads, size_t smem)
+{
+    auto kfn = wfa_quadg_kernel<BT, MAXT>;
+    int n = 0;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
+    return n;
+}
+
+/* three register budgets: <= 512 threads (107 registers), <= 768 (85), <= 1024 (64) */
+cudaError_t launch_quadg(const KernelParams &p, int threads, int ctas, size_t smem_bytes, cudaStream_t s)
+{
+    if (!p.gring) return cudaErrorInvalidValue;
+    if (threads <= 512) return p.with_bt ? launch_quadg_one<true, 512>(p, threads, ctas, smem_bytes, s) : launch_quadg_one<false, 512>(p, threads, ctas, smem_bytes, s);
+    if (threads <= 768) return p.with_bt ? launch_quadg_one<true, 768>(p, threads, ctas, smem_bytes, s) : launch_quadg_one<false, 768>(p, threads, ctas, smem_bytes, s);
+    return p.with_bt ? launch_quadg_one<true, 1024>(p, threads, ctas, smem_bytes, s) : launch_quadg_one<false, 1024>(p, threads, ctas, smem_bytes, s);
+}
+
+int quadg_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt)
+{
+    if (threads <= 512) return bt ? occupancy_quadg_one<true, 512>(threads, smem_bytes) : occupancy_quadg_one<false, 512>(threads, smem_bytes);
+    if (threads <= 768) return bt ? occupancy_quadg_one<true, 768>(threads, smem_bytes) : occupancy_quadg_one<false, 768>(threads, smem_bytes);
+    return bt ? occupancy_quadg_one<true, 1024>(threads, smem_bytes) : occupancy_quadg_one<false, 1024>(threads, smem_bytes);
 }
 
 cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_per_cta, int ctas,

@@ -117,6 +117,10 @@ cudaError_t launch_exact(const KernelParams &p, int group_threads, int groups_pe
  * aligned; with backtrace it writes ring snapshots: p.ck_off must be set) */
 cudaError_t launch_quad(const KernelParams &p, int threads, int ctas, size_t smem_bytes, cudaStream_t s);
 int quad_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt);
+/* large tier: int32 rings in global memory (p.gring, rows of p.row_stride elements, multiple of 4, diagonal 0 at p.center,
+ * multiple of 4), four diagonals per thread; shared memory = exact_smem_bytes(A, E1, 0, seq_words, 1, 1, true) */
+cudaError_t launch_quadg(const KernelParams &p, int threads, int ctas, size_t smem_bytes, cudaStream_t s);
+int quadg_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt);
 /* per-pair score upper bounds for the pruning (warp per pair) */
 cudaError_t launch_bound(const KernelParams &p, int ctas, int warps, cudaStream_t s);
 size_t bound_smem_bytes(int A, int E1, int warps);
