@@ -18,13 +18,13 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 FAMILIES = {
     #           pairs, length, err, max_error, cigar, band, width, env
     "warp":       (192, 150, 0.04, 50, True, -1, 0, {}),
-    "cta":        (40, 1000, 0.10, 400, True, -1, 0, {}),
-    "score":      (40, 1000, 0.10, 400, False, -1, 0, {}),
+    "cta":        (40, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_QUAD_MIN": "1"}),
+    "score":      (40, 1000, 0.10, 400, False, -1, 0, {"WFAGPU_QUAD_MIN": "1"}),
     "banded":     (24, 2000, 0.05, 400, True, 10, 128, {}),
     "large":      (12, 600, 0.08, 200, True, -1, 0, {"WFAGPU_FORCE_LARGE": "1"}),
     "ascii":      (24, 400, 0.05, 100, True, -1, 0, {}),
     "redispatch": (32, 800, 0.10, 40, True, -1, 0, {}),
-    "quad_pairs": (40, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_QUAD_PAIRS": "1"}),      # two scores per barrier interval
+    "quad_pairs": (40, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_QUAD_PAIRS": "1", "WFAGPU_QUAD_MIN": "1"}),      # two scores per barrier interval
     "one_diag":   (24, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_NO_QUAD": "1"}),         # one diagonal per thread (the -c path)
     "workers":    (96, 600, 0.06, 200, True, -1, 0, {"WFAGPU_DEVICES": "0,0"}),        # two workers, one GPU
 }

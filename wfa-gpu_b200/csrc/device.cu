@@ -194,6 +194,7 @@ struct wfagpu_device {
     bool device_text = true;   /* WFAGPU_HOST_CIGAR=1 leaves the text to the host */
     bool leased = false;       /* handed out by wfagpu_device_open and not released yet */
     bool independent = false;  /* wfagpu_device_rescore in progress: do not learn hints from it */
+    int quad_min = 256;        /* smallest ring half width that runs the four-diagonals-per-thread kernel */
     int hint_margin_pm = 83, hint_min_pm = 31;   /* provisioning margins over the last batch's largest score, per mille */
     int max_steps_cap = 60000; /* most wavefront steps a pair may take (WFAGPU_MAX_STEPS_CAP lowers it: tests) */
 };
@@ -297,6 +298,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->use_hint = env_int("WFAGPU_NO_HINT", 0) == 0;
     d->force_large = env_int("WFAGPU_FORCE_LARGE", 0) != 0;
     d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;
+    d->quad_min = std::max(1, env_int("WFAGPU_QUAD_MIN", 256));
     d->hint_margin_pm = std::max(0, env_int("WFAGPU_HINT_MARGIN_PM", 83));
     d->hint_min_pm = std::min(d->hint_margin_pm, std::max(0, env_int("WFAGPU_HINT_MIN_PM", 31)));
     d->max_steps_cap = std::min(60000, std::max(16, env_int("WFAGPU_MAX_STEPS_CAP", 60000)));
@@ -489,7 +491,9 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
         c->groups_per_cta = 1;
         c->ckpt = bt && !d->no_ckpt;
         /* packed pairs on shared-memory rings run four diagonals per thread (with backtrace: snapshots only) */
-        c->quad = !ascii && !d->no_quad && (!bt || c->ckpt);
+        /* (measured on B200: 1 kbp / 10 %, ring half width 196: 9.5 ms per 50 k pairs with one diagonal per thread and 16 CTAs per
+         * SM against 11.0 ms; from a half width of ~300 on the four-diagonal kernel wins) */
+        c->quad = !ascii && !d->no_quad && (!bt || c->ckpt) && n_want >= d->quad_min;
         /* two scores per barrier: score d + 1 must not read the extended M of score d (x >= 2, o + e >= 2) and takes
          * its extend sources from registers (e == 1); costs one more row per ring */
         c->quad_pairs = c->quad && !d->no_quad_pairs && x >= 2 && o + e >= 2 && e == 1;
