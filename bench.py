@@ -373,7 +373,7 @@ def run_configs(wfagpu):
         {"banded_recall": round(recall, 5), "note": "recall = pairs whose banded score equals the exact score"})
     release(a)
     # cfg 5: 50 kbp, 15 %, CIGAR, first budget (8000) below every score: every pair is re-dispatched on the GPU
-    n5 = int(os.environ.get("WFAGPU_BENCH_CFG5_PAIRS", 256))
+    n5 = int(os.environ.get("WFAGPU_BENCH_CFG5_PAIRS", 2500))     # BASELINE: 20 000 pairs over 8 GPUs
     a = make_aligner(wfagpu, 0xB2000005, n5, 50000, 0.15, 0.15, PEN, max_error=8000, cigar=True)
     dt, st = time_align(a, 1, warm=1)
     par = parity_sample(a, list(range(0, n5, max(1, n5 // 8)))[:8], PEN, "cpu_wfa_score", orc, refcpu, 8000) if refcpu else "reference CPU WFA not built"
@@ -383,7 +383,7 @@ def run_configs(wfagpu):
         p, t = a.pair(i)
         bad_cigar += 0 if a.L.wfagpu_check_result(p.encode(), len(p), t.encode(), len(t), pen, a.error(i), a.cigar(i).encode()) else 1
     out["cfg5_50kbp_15pct_cigar_redispatch"] = entry(a, dt, st, par, {"invalid_cigars_in_sample": bad_cigar,
-                                                                      "note": f"{n5} pairs per GPU (BASELINE: 20 000 over 8 GPUs); the reference GPU code cannot run it (int16 offsets)"})
+                                                                      "note": f"{n5} pairs on one GPU = one GPU's share of BASELINE's 20 000 over 8; the reference GPU code cannot run it (int16 offsets)"})
     a.destroy()
     return out
 
