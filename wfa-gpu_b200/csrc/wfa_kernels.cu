@@ -6,6 +6,20 @@
 
 namespace wfagpu {
 
+/* Every kernel may use up to the opt-in maximum of dynamic shared memory (227 KB on B200).  The limit is a per-function,
+ * per-device attribute: it is always set to the same value, never to the size of one launch, because two host threads that
+ * drive the same GPU (two workers of one call, or two calls) would otherwise lower it under each other's launches. */
+template <typename K>
+static cudaError_t allow_max_smem(K kfn)
+{
+    int dev = 0, optin = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (err != cudaSuccess) return err;
+    return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+}
+
 /* ======================================================================== */
 /*                               PTX helpers                                */
 /* ======================================================================== */
@@ -2282,7 +2296,7 @@ template <bool ASCII, bool BT>
 static cudaError_t launch_banded_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
     auto kfn = wfa_banded_kernel<ASCII, BT>;
-    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = allow_max_smem(kfn);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, threads, smem, s>>>(p);
     return cudaGetLastError();
@@ -2293,7 +2307,7 @@ static int occupancy_banded_one(int threads, size_t smem)
 {
     auto kfn = wfa_banded_kernel<ASCII, BT>;
     int n = 0;
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (allow_max_smem(kfn) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
     return n;
 }
@@ -2461,7 +2475,7 @@ template <bool WARP, bool ASCII, bool BT, typename R = RingS16, bool CKPT = fals
 static cudaError_t launch_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
     auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R, CKPT>;
-    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = allow_max_smem(kfn);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, threads, smem, s>>>(p);
     return cudaGetLastError();
@@ -2472,7 +2486,7 @@ static int occupancy_one(int threads, size_t smem)
 {
     auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R, CKPT>;
     int n = 0;
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (allow_max_smem(kfn) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
     return n;
 }
@@ -2491,7 +2505,7 @@ size_t bound_smem_bytes(int A, int E1, int warps) { return (size_t)warps * (size
 cudaError_t launch_bound(const KernelParams &p, int ctas, int warps, cudaStream_t s)
 {
     const size_t smem = bound_smem_bytes(p.A, p.E1, warps);
-    cudaError_t err = cudaFuncSetAttribute(wfa_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = allow_max_smem(wfa_bound_kernel);
     if (err != cudaSuccess) return err;
     wfa_bound_kernel<<<ctas, 32 * warps, smem, s>>>(p);
     return cudaGetLastError();
@@ -2501,7 +2515,7 @@ int bound_max_ctas_per_sm(int A, int E1, int warps)
 {
     const size_t smem = bound_smem_bytes(A, E1, warps);
     int n = 0;
-    if (cudaFuncSetAttribute(wfa_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (allow_max_smem(wfa_bound_kernel) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfa_bound_kernel, 32 * warps, smem) != cudaSuccess) return 0;
     return n;
 }
@@ -2529,7 +2543,7 @@ cudaError_t launch_traceback(const KernelParams &p, int ctas, int warps, bool as
     const size_t smem = traceback_smem_bytes(p.A, p.ck_period, warps);
     tb_kernel_t kfn = traceback_fn(ascii, p.ck_period);
     if (!kfn) return cudaErrorInvalidValue;
-    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = allow_max_smem(kfn);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, 32 * warps, smem, s>>>(p);
     return cudaGetLastError();
@@ -2541,7 +2555,7 @@ int traceback_max_ctas_per_sm(int A, int period, int warps, bool ascii)
     tb_kernel_t kfn = traceback_fn(ascii, period);
     int n = 0;
     if (!kfn) return 0;
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (allow_max_smem(kfn) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, 32 * warps, smem) != cudaSuccess) return 0;
     return n;
 }
@@ -2556,7 +2570,7 @@ template <bool BT, bool COUNT>
 static cudaError_t launch_quad_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
     auto kfn = wfa_quad_kernel<BT, COUNT>;
-    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = allow_max_smem(kfn);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, threads, smem, s>>>(p);
     return cudaGetLastError();
@@ -2575,11 +2589,11 @@ int quad_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt)
     int n = 0;
     if (bt) {
         auto kfn = wfa_quad_kernel<true, false>;
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;
+        if (allow_max_smem(kfn) != cudaSuccess) return 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
     } else {
         auto kfn = wfa_quad_kernel<false, false>;
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;
+        if (allow_max_smem(kfn) != cudaSuccess) return 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
     }
     return n;
@@ -2589,7 +2603,7 @@ template <bool BT, int MAXT>
 static cudaError_t launch_quadg_one(const KernelParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
     auto kfn = wfa_quadg_kernel<BT, MAXT>;
-    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = allow_max_smem(kfn);
     if (err != cudaSuccess) return err;
     kfn<<<ctas, threads, smem, s>>>(p);
     return cudaGetLastError();
@@ -2599,7 +2613,7 @@ static int occupancy_quadg_one(int threads, size_t smem)
 {
     auto kfn = wfa_quadg_kernel<BT, MAXT>;
     int n = 0;
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (allow_max_smem(kfn) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
     return n;
 }
