@@ -510,16 +510,24 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
         /* n_min <= n_want: the rings may be provisioned below n_want (down to n_min) when that buys
          * another resident CTA -- the few pairs that then outgrow them are re-dispatched */
         n_min = std::max(1, std::min(n_min, n_want));
+        /* do k CTAs of the smallest shape really fit with this much dynamic shared memory?  The arithmetic budget below is
+         * a first filter; the runtime's occupancy calculator decides (allocation granularity: a ring 6 diagonals wider than
+         * the arithmetic allowed cost rank 3 of an 8-GPU run its fifth CTA per SM, 33.4 instead of 29.2 ms per step) */
+        auto fits = [&](int k, size_t bytes, size_t budget) {
+            if (bytes > budget) return false;
+            const int occ_k = c->quad ? quad_max_ctas_per_sm(64, bytes, bt) : exact_max_ctas_per_sm(64, 1, bytes, ascii, bt, c->ckpt);
+            return occ_k >= k;
+        };
         for (int k = kmax; k >= 1 && !best_k; --k) {
             /* every resident CTA also reserves 1 KB of system shared memory */
             const size_t budget = std::min(smem_max, smem_sm / k - 1024);
             for (int st = 2; st >= 1; --st) {
                 if (d->force_stages && st != d->force_stages) continue;
-                if (exact_smem_bytes(RA, RE, rs(n_min), seq_words, 1, st, true) > budget) continue;
+                if (!fits(k, exact_smem_bytes(RA, RE, rs(n_min), seq_words, 1, st, true), budget)) continue;
                 int lo = n_min, hi = n_want;             /* widest rings that still fit k CTAs */
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) / 2;
-                    if (exact_smem_bytes(RA, RE, rs(mid), seq_words, 1, st, true) <= budget) lo = mid; else hi = mid - 1;
+                    if (fits(k, exact_smem_bytes(RA, RE, rs(mid), seq_words, 1, st, true), budget)) lo = mid; else hi = mid - 1;
                 }
                 best_k = k; stages = st; n_cap = lo;
                 smem = exact_smem_bytes(RA, RE, rs(n_cap), seq_words, 1, st, true);
