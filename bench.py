@@ -534,6 +534,26 @@ def run_ours(args):
                 big.destroy()
             except Exception as e:                                        # pragma: no cover
                 e2e_inlib = {"error": str(e)[:300]}
+            # BASELINE config 5 at its stated size on N GPUs: 2500 pairs per GPU (20 000 on 8) of 50 kbp / 15 % in ONE call
+            if not args.quick and not args.no_configs:
+                try:
+                    n5 = int(os.environ.get("WFAGPU_BENCH_CFG5_PAIRS", 2500)) * world
+                    a5 = make_aligner(wfagpu, 0xB2000005, n5, 50000, 0.15, 0.15, PEN, max_error=8000, cigar=True)
+                    wfagpu.set_devices(f"n:{world}")
+                    dt5, st5 = time_align(a5, 1, warm=1)
+                    wfagpu.set_devices(str(local))
+                    pen5 = wfagpu.AffinePenalties(*PEN)
+                    bad5 = 0
+                    for i in range(0, n5, max(1, n5 // 32)):
+                        p5, t5 = a5.pair(i)
+                        bad5 += 0 if lib.wfagpu_check_result(p5.encode(), len(p5), t5.encode(), len(t5), pen5, a5.error(i), a5.cigar(i).encode()) else 1
+                    e2e_inlib["cfg5_50kbp_15pct_cigar_redispatch"] = {
+                        "pairs": n5, "devices": int(st5["devices"]), "e2e_alignments_per_s": round(n5 / dt5, 1), "e2e_gcups": round(gcells(a5) / dt5 / 1e9, 1),
+                        "wall_ms": round(dt5 * 1e3, 1), "redispatched": int(st5["redispatched"]), "failed_pairs": int(st5["failed_pairs"]),
+                        "invalid_cigars_in_sample": bad5, "note": "ONE wfagpu_align call sharded in-library; first budget 8000 below every score"}
+                    a5.destroy()
+                except Exception as e:                                    # pragma: no cover
+                    e2e_inlib["cfg5_50kbp_15pct_cigar_redispatch"] = {"error": str(e)[:300]}
             if store is not None:
                 store.set("wfagpu_inlib_done", "1")
         elif store is not None:

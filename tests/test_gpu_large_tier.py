@@ -48,3 +48,22 @@ def test_sequences_longer_than_32767(oracle, refcpu):
         assert a.error(i) == errs[i]
         assert oracle.cigar_score(p, t, a.cigar(i), 2, 3, 1) == errs[i]
     assert a.run_stats()["redispatched"] >= a.num_pairs
+
+
+def test_config5_shape_on_64_pairs_matches_cpu_wfa(oracle, refcpu):
+    # BASELINE config 5 (50 kbp, 15 %, CIGAR, first budget 8000 below every score: every pair is re-dispatched on the GPU
+    # with a bound-guided budget) on 64 pairs: every score == the unmodified reference CPU WFA, every CIGAR an alignment of
+    # exactly that cost; the re-dispatched pass runs wfa_quadg_kernel (int32 rings in L2)
+    a = synth_aligner([(64, 50000, 0.15, 0.15)], 0xB2000005)
+    assert a.initialize_parameters(2, 3, 1)
+    a.options.compute_cigar = True
+    a.options.max_error = 8000
+    a.align()
+    st = a.run_stats()
+    assert st["redispatched"] == 64 and st["failed_pairs"] == 0
+    pairs = [a.pair(i) for i in range(a.num_pairs)]
+    errs, _ = refcpu.align_batch([p for p, _ in pairs], [t for _, t in pairs], 2, 3, 1, cigar=False,
+                                 threads=len(os.sched_getaffinity(0)))
+    assert a.errors() == list(errs)
+    for i, (p, t) in enumerate(pairs):
+        assert oracle.cigar_score(p, t, a.cigar(i), 2, 3, 1) == errs[i]
