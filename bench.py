@@ -441,6 +441,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = wfagpu.load()
     wfagpu.set_devices(str(local))
+    # torchrun pins OMP_NUM_THREADS=1 per rank; the library's result loop may use this rank's share of the host cores
+    wfagpu.set_host_threads(max(1, min(4, len(os.sched_getaffinity(0)) // max(1, world))))
 
     a = make_aligner(wfagpu, shard_seed(rank), PAIRS_PER_GPU, LENGTH, ERR, ERR, PEN, max_error=MAX_ERROR, cigar=True)
     gcells_total = gcells(a)
@@ -517,6 +519,9 @@ def run_ours(args):
     # ---------------- (N > 1) one wfagpu_align call sharding over the N GPUs in-library -------------
     e2e_inlib = None
     if world > 1:
+        # every rank gives its device memory back first (pooled contexts keep ~40 GB of snapshot arenas per GPU)
+        lib.wfagpu_device_close_all()
+        barrier()
         try:
             store = dist.distributed_c10d._get_default_store()      # host-side wait: no NCCL kernel spins on the idle GPUs
         except Exception:                                            # pragma: no cover
@@ -714,7 +719,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 1), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3 / args.steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": config({"pairs_per_step": n}), "gcups": round(gc, 2),
+        "config": config({"parallelism": f"pairs sharded over {world} GPU(s), no collective"}), "sample_pairs_per_step": n,
+        "gcups": round(gc, 2),
         "cpu_baseline": {"value": round(v, 1), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(v, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
