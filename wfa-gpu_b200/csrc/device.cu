@@ -188,7 +188,7 @@ struct wfagpu_device {
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
     int hint_dist = 0;
     double hint_mean = 0;              /* mean score of the finished pairs of that batch */
-    int hint_key[3] = {-1, -1, -1};
+    int hint_key[4] = {-1, -1, -1, -1};   /* x, o, e, length class (log2 of the longest sequence) */
     bool use_hint = true;
     bool force_large = false;
     bool device_text = true;   /* WFAGPU_HOST_CIGAR=1 leaves the text to the host */
@@ -207,11 +207,19 @@ struct DevShared {
     int dev = -1;
     int hint_dist = 0;
     double hint_mean = 0;
-    int hint_key[3] = {-1, -1, -1};
+    int hint_key[4] = {-1, -1, -1, -1};
 };
 static std::mutex g_mu;
 static std::vector<wfagpu_device *> g_devices;
 static std::vector<DevShared> g_shared;
+
+/* a hint learnt on 150 bp reads says nothing about 10 kbp reads: hints are only used within a length class */
+static int length_class(uint32_t max_len)
+{
+    int c = 0;
+    while (max_len > 1) { max_len >>= 1; ++c; }
+    return c;
+}
 
 static DevShared &shared_of(int dev)          /* g_mu held */
 {
@@ -227,7 +235,7 @@ static void pull_hint(wfagpu_device *d)
     const DevShared &h = shared_of(d->dev);
     d->hint_dist = d->use_hint ? h.hint_dist : 0;
     d->hint_mean = h.hint_mean;
-    d->hint_key[0] = h.hint_key[0]; d->hint_key[1] = h.hint_key[1]; d->hint_key[2] = h.hint_key[2];
+    for (int i = 0; i < 4; ++i) d->hint_key[i] = h.hint_key[i];
 }
 static void push_hint(wfagpu_device *d)
 {
@@ -235,7 +243,7 @@ static void push_hint(wfagpu_device *d)
     DevShared &h = shared_of(d->dev);
     h.hint_dist = d->hint_dist;
     h.hint_mean = d->hint_mean;
-    h.hint_key[0] = d->hint_key[0]; h.hint_key[1] = d->hint_key[1]; h.hint_key[2] = d->hint_key[2];
+    for (int i = 0; i < 4; ++i) h.hint_key[i] = d->hint_key[i];
 }
 
 static int env_int(const char *name, int dflt)
@@ -595,7 +603,7 @@ static void learn_hint(wfagpu_device *d, Slot &s, size_t n)
         }
     d->hint_dist = d->use_hint ? dmax : 0;
     d->hint_mean = cnt ? sum / (double)cnt : 0;
-    d->hint_key[0] = s.plan.x; d->hint_key[1] = s.plan.o; d->hint_key[2] = s.plan.e;
+    d->hint_key[0] = s.plan.x; d->hint_key[1] = s.plan.o; d->hint_key[2] = s.plan.e; d->hint_key[3] = length_class(s.max_len);
     push_hint(d);
 }
 
@@ -703,7 +711,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
      * pruning), so the rings only have to hold max_d min(n_d, kt_max + (d_end - 1 - d) / e). */
     int d_want = d_full;
     bool hinted = false;
-    if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e) {
+    if (use_hint && plan.band <= 0 && d->hint_dist > 0 && d->hint_key[0] == plan.x && d->hint_key[1] == plan.o && d->hint_key[2] == plan.e &&
+        d->hint_key[3] == length_class(s.max_len)) {
         d_want = (int)std::min<long long>((long long)d->hint_dist + (long long)d->hint_dist * d->hint_margin_pm / 1000 + 8, d_full - 1) + 1;
         hinted = d_want < d_full;
     }
