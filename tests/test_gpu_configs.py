@@ -55,17 +55,39 @@ def test_config2_1M_pairs_150bp_score_only(refcpu):
         assert got[lo:lo + 250000] == cpu_scores(refcpu, a, lo, min(lo + 250000, a.num_pairs))
 
 
-def test_config3_100k_pairs_1kbp_cigar_with_redispatch(oracle, refcpu):
+def test_config3_100k_pairs_1kbp_cigar_with_redispatch(oracle, refcpu, monkeypatch):
+    # -e 300: ~4 % of the pairs score above it.  First with the budget lift off (every chunk re-dispatches them on the GPU),
+    # then with the default policy (a fresh process-wide hint: the first chunks re-dispatch, later chunks and the second call
+    # run their first pass with the budget the last batch needed) -- same results either way
     a = synth_aligner([(100000, 1000, 0.10, 0.10)], 0xB2000003)
     assert a.initialize_parameters(*PEN)
     a.options.compute_cigar = True
-    a.options.max_error = 300                                # ~4 % of the pairs score above it: re-dispatched on the GPU
-    a.align()
-    st = a.run_stats()
-    assert st["redispatched"] > 1000 and st["failed_pairs"] == 0
-    assert a.errors() == cpu_scores(refcpu, a, 0, a.num_pairs)
-    assert check_cigars(a, range(0, a.num_pairs, 7)) == 0
-    for i in range(0, a.num_pairs, 5003):
-        p, t = a.pair(i)
-        r = oracle.align(p, t, *PEN, 100000)
-        assert (a.error(i), a.cigar(i)) == (r["distance"], r["cigar"])
+    a.options.max_error = 300
+    monkeypatch.setenv("WFAGPU_HINT_LIFT_PM", "0")
+    wfagpu.load().wfagpu_device_close_all()                  # forget hints, contexts re-read the environment
+    try:
+        a.align()
+        st = a.run_stats()
+        assert st["redispatched"] > 1000 and st["failed_pairs"] == 0
+        want = cpu_scores(refcpu, a, 0, a.num_pairs)
+        assert a.errors() == want
+        assert check_cigars(a, range(0, a.num_pairs, 7)) == 0
+        for i in range(0, a.num_pairs, 5003):
+            p, t = a.pair(i)
+            r = oracle.align(p, t, *PEN, 100000)
+            assert (a.error(i), a.cigar(i)) == (r["distance"], r["cigar"])
+        unlifted = [(a.error(i), a.cigar(i)) for i in range(0, a.num_pairs, 11)]
+        monkeypatch.delenv("WFAGPU_HINT_LIFT_PM")
+        wfagpu.load().wfagpu_device_close_all()
+        a.reset_results()
+        a.align()
+        first = a.run_stats()["redispatched"]
+        a.reset_results()
+        a.align()
+        st = a.run_stats()
+        assert st["redispatched"] < first and st["redispatched"] < 200 and st["failed_pairs"] == 0
+        assert a.errors() == want
+        assert [(a.error(i), a.cigar(i)) for i in range(0, a.num_pairs, 11)] == unlifted
+    finally:
+        monkeypatch.undo()
+        wfagpu.load().wfagpu_device_close_all()

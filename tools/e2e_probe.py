@@ -12,7 +12,7 @@ a.add_synthetic(0xB2000004, n, L, err, err)
 a.initialize_parameters(2, 3, 1)
 a.options.max_error = me
 a.options.compute_cigar = bool(cigar)
-a.set_batch_size(batch)
+a.set_batch_size(batch) if batch < n else None
 a.pin_host_buffers()
 a.align()
 ts = []

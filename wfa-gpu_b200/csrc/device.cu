@@ -122,6 +122,9 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool wf_timed = false;             /* ev[6], ev[7] bracket the first pass's wavefront kernel */
+    cudaEvent_t ev_tab = nullptr;      /* after the last upload of a host-built table (step table, snapshot offsets) */
+    bool tab_inflight = false;
+    int first_steps = 0;               /* wavefront-step budget the first pass of this batch ran with (>= plan.max_steps) */
     DevBuf<char> ascii;
     DevBuf<uint32_t> packed;
     DevBuf<wfagpu_pair_t> pairs;
@@ -196,6 +199,7 @@ struct wfagpu_device {
     bool independent = false;  /* wfagpu_device_rescore in progress: do not learn hints from it */
     int quad_min = 256;        /* smallest ring half width that runs the four-diagonals-per-thread kernel */
     int hint_margin_pm = 83, hint_min_pm = 31;   /* provisioning margins over the last batch's largest score, per mille */
+    int hint_lift_pm = 250;    /* the first pass may exceed the -e budget by this much when the last batch needed it (0 = never) */
     int max_steps_cap = 60000; /* most wavefront steps a pair may take (WFAGPU_MAX_STEPS_CAP lowers it: tests) */
 };
 
@@ -287,6 +291,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
             return nullptr;
         }
         for (auto &ev : s.ev) cudaEventCreate(&ev);
+        cudaEventCreateWithFlags(&s.ev_tab, cudaEventDisableTiming);
     }
     d->count_cells = env_int("WFAGPU_COUNT_CELLS", 0) != 0;
     d->force_threads = env_int("WFAGPU_THREADS", 0);
@@ -309,6 +314,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->quad_min = std::max(1, env_int("WFAGPU_QUAD_MIN", 256));
     d->hint_margin_pm = std::max(0, env_int("WFAGPU_HINT_MARGIN_PM", 83));
     d->hint_min_pm = std::min(d->hint_margin_pm, std::max(0, env_int("WFAGPU_HINT_MIN_PM", 31)));
+    d->hint_lift_pm = std::max(0, env_int("WFAGPU_HINT_LIFT_PM", 250));
     d->max_steps_cap = std::min(60000, std::max(16, env_int("WFAGPU_MAX_STEPS_CAP", 60000)));
     d->leased = true;
     g_devices.push_back(d);
@@ -337,6 +343,7 @@ extern "C" void wfagpu_device_close_all(void)
             s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
             s.h_counters.release(); s.h_cells.release(); s.h_steps.release();
             for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
+            if (s.ev_tab) cudaEventDestroy(s.ev_tab);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         delete d;
@@ -607,6 +614,23 @@ static void learn_hint(wfagpu_device *d, Slot &s, size_t n)
     push_hint(d);
 }
 
+/* The host-built tables are uploaded from pinned memory that the next pass rewrites.  Waiting for the last such upload
+ * (an event) is enough; waiting for the whole stream would also wait for the chunk's own sequence upload and pack, which
+ * a first pass has just queued (0.5 ms per 12500 x 1 kbp chunk whenever first pass and re-dispatch budgets alternate). */
+static int tables_idle(Slot &s)
+{
+    if (!s.tab_inflight) return 0;
+    if (s.ev_tab) CK(cudaEventSynchronize(s.ev_tab)); else CK(cudaStreamSynchronize(s.stream));
+    s.tab_inflight = false;
+    return 0;
+}
+static int tables_sent(Slot &s)
+{
+    if (s.ev_tab) CK(cudaEventRecord(s.ev_tab, s.stream));
+    s.tab_inflight = true;
+    return 0;
+}
+
 /* Ring-snapshot layout of the checkpointed traceback for period P: snapshot j (score j * P) holds
  * (A-1) + 2e rows of the 16-byte units that cover [-n, n] at that score.  h_ck_off[j] = units used
  * by the snapshots before j. */
@@ -619,7 +643,7 @@ static int ensure_ck_table(Slot &s, const wfagpu_plan_t &plan, int period)
     const int n_ck = (de - 1) / period + 2;
     s.h_ck_off.assign((size_t)n_ck + 1, 0);
     if (s.h_ck32.ensure((size_t)n_ck + 1)) return -1;
-    CK(cudaStreamSynchronize(s.stream));      /* an earlier pass may still be reading the pinned copy */
+    if (tables_idle(s)) return -1;            /* an earlier pass may still be reading the pinned copy */
     uint64_t acc = 0;
     s.h_ck32.p[0] = 0;
     for (int j = 1; j <= n_ck; ++j) {
@@ -633,6 +657,7 @@ static int ensure_ck_table(Slot &s, const wfagpu_plan_t &plan, int period)
     }
     if (s.ck_off.ensure((size_t)n_ck + 1)) return -1;
     CK(cudaMemcpyAsync(s.ck_off.p, s.h_ck32.p, ((size_t)n_ck + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    if (tables_sent(s)) return -1;
     s.ck_key[0] = period;
     return 0;
 }
@@ -646,12 +671,13 @@ static int ensure_step_table(Slot &s, const wfagpu_plan_t &plan, int max_steps)
         s.tab_key[4] == tab_win)
         return 0;
     if (s.h_steps.ensure((size_t)max_dist + 1)) return -1;
-    CK(cudaStreamSynchronize(s.stream));  /* a previous pass may still be reading the pinned table */
+    if (tables_idle(s)) return -1;        /* a previous pass may still be reading the pinned table */
     uint64_t units = 0;
     const int de = wfagpu_build_step_table(plan.x, plan.o, plan.e, max_steps, max_dist, tab_win, s.h_steps.p, &units);
     if (de < 1) return -1;
     if (s.steps.ensure((size_t)de + 1)) return -1;
     CK(cudaMemcpyAsync(s.steps.p, s.h_steps.p, (size_t)de * sizeof(wfagpu_step_t), cudaMemcpyHostToDevice, s.stream));
+    if (tables_sent(s)) return -1;
     s.tab_key[0] = plan.x; s.tab_key[1] = plan.o; s.tab_key[2] = plan.e; s.tab_key[3] = max_steps; s.tab_key[4] = tab_win;
     s.tab_d_end = de;
     s.tab_arena_units = units;
@@ -1053,7 +1079,19 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
     CK(cudaEventRecord(s.ev[3], s.stream));
     s.last_d_end = 0;
     s.wf_timed = false;
-    int rc = launch_pass(d, s, *plan, plan->max_steps, s.order.p, n, s.retry[0].p, false, true, true, &s.capped);
+    /* -e is where the reference hands a pair to its CPU aligner (lib/align.cu:237); here such pairs cost a second pass on the
+     * GPU.  When the last batch of this kind needed scores a little beyond -e (at most a quarter more), the first pass is
+     * given that budget straight away: 100 k x 1 kbp / 10 % with -e 300 re-dispatched 4.4 % of its pairs in every chunk. */
+    int first_steps = plan->max_steps;
+    pull_hint(d);
+    if (plan->band <= 0 && d->hint_dist > 0 && d->hint_lift_pm > 0 && d->hint_key[0] == plan->x && d->hint_key[1] == plan->o &&
+        d->hint_key[2] == plan->e && d->hint_key[3] == length_class(s.max_len)) {
+        const long long want = (long long)d->hint_dist + (long long)d->hint_dist * d->hint_margin_pm / 1000 + 12;
+        const long long most = (long long)plan->max_steps + (long long)plan->max_steps * d->hint_lift_pm / 1000;
+        if (want > first_steps && d->hint_dist <= most) first_steps = (int)std::min<long long>(want, d->max_steps_cap);
+    }
+    s.first_steps = first_steps;
+    int rc = launch_pass(d, s, *plan, first_steps, s.order.p, n, s.retry[0].p, false, true, true, &s.capped);
     if (rc) return rc;
     d->device_text = env_int("WFAGPU_HOST_CIGAR", 0) == 0;   /* re-read: tests flip it between runs */
     if (plan->with_cigar && d->device_text && enqueue_text(d, s, n, s.last_d_end)) return -1;
@@ -1164,7 +1202,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
         }
         return 0;
     };
-    int rc = redispatch(false, plan.max_steps, s.capped);
+    int rc = redispatch(false, std::max(plan.max_steps, s.first_steps), s.capped);
     if (rc) return rc;
 
     /* ---- pairs with non-ACGT bytes: byte-compare kernel on the ASCII copy ---- */

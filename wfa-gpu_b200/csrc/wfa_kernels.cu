@@ -4,20 +4,72 @@
  */
 #include "wfa_kernels.cuh"
 
+#include <mutex>
+#include <unordered_map>
+#include <unordered_set>
+
 namespace wfagpu {
 
 /* Every kernel may use up to the opt-in maximum of dynamic shared memory (227 KB on B200).  The limit is a per-function,
  * per-device attribute: it is always set to the same value, never to the size of one launch, because two host threads that
  * drive the same GPU (two workers of one call, or two calls) would otherwise lower it under each other's launches. */
+struct LaunchMemo {                /* what the host already asked the runtime, per device and kernel */
+    std::mutex mu;
+    std::unordered_set<uint64_t> smem_allowed;
+    std::unordered_map<uint64_t, int> occupancy;
+};
+static LaunchMemo &launch_memo() { static LaunchMemo m; return m; }
+
+static inline uint64_t memo_key(int dev, const void *kfn, uint64_t a, uint64_t b)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ull * (uint64_t)(uintptr_t)kfn + (uint64_t)dev;
+    h = (h ^ (h >> 29)) * 0xBF58476D1CE4E5B9ull + a;
+    h = (h ^ (h >> 32)) * 0x94D049BB133111EBull + b;
+    return h ^ (h >> 31);
+}
+
 template <typename K>
 static cudaError_t allow_max_smem(K kfn)
 {
     int dev = 0, optin = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
+    LaunchMemo &m = launch_memo();
+    const uint64_t key = memo_key(dev, (const void *)kfn, 0, 0);
+    {
+        std::lock_guard<std::mutex> g(m.mu);
+        if (m.smem_allowed.count(key)) return cudaSuccess;
+    }
     err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (err != cudaSuccess) return err;
-    return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (err != cudaSuccess) return err;
+    std::lock_guard<std::mutex> g(m.mu);
+    m.smem_allowed.insert(key);
+    return cudaSuccess;
+}
+
+/* cudaOccupancyMaxActiveBlocksPerMultiprocessor, remembered: the chunk planner asks the same few questions for every chunk
+ * of a stream (10-20 us each, several dozen per pass). */
+template <typename K>
+static cudaError_t occupancy_of(int *n, K kfn, int threads, size_t smem)
+{
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    LaunchMemo &m = launch_memo();
+    const uint64_t key = memo_key(dev, (const void *)kfn, (uint64_t)threads, (uint64_t)smem + 1);
+    {
+        std::lock_guard<std::mutex> g(m.mu);
+        auto it = m.occupancy.find(key);
+        if (it != m.occupancy.end()) { *n = it->second; return cudaSuccess; }
+    }
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kfn, threads, smem);
+    if (err != cudaSuccess) return err;
+    std::lock_guard<std::mutex> g(m.mu);
+    if (m.occupancy.size() > 65536) m.occupancy.clear();
+    m.occupancy[key] = *n;
+    return cudaSuccess;
 }
 
 /* ======================================================================== */
@@ -2308,7 +2360,7 @@ static int occupancy_banded_one(int threads, size_t smem)
     auto kfn = wfa_banded_kernel<ASCII, BT>;
     int n = 0;
     if (allow_max_smem(kfn) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
+    if (occupancy_of(&n, kfn, threads, smem) != cudaSuccess) return 0;
     return n;
 }
 
@@ -2487,7 +2539,7 @@ static int occupancy_one(int threads, size_t smem)
     auto kfn = wfa_exact_kernel<WARP, ASCII, BT, R, CKPT>;
     int n = 0;
     if (allow_max_smem(kfn) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
+    if (occupancy_of(&n, kfn, threads, smem) != cudaSuccess) return 0;
     return n;
 }
 
@@ -2516,7 +2568,7 @@ int bound_max_ctas_per_sm(int A, int E1, int warps)
     const size_t smem = bound_smem_bytes(A, E1, warps);
     int n = 0;
     if (allow_max_smem(wfa_bound_kernel) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfa_bound_kernel, 32 * warps, smem) != cudaSuccess) return 0;
+    if (occupancy_of(&n, wfa_bound_kernel, 32 * warps, smem) != cudaSuccess) return 0;
     return n;
 }
 
@@ -2556,7 +2608,7 @@ int traceback_max_ctas_per_sm(int A, int period, int warps, bool ascii)
     int n = 0;
     if (!kfn) return 0;
     if (allow_max_smem(kfn) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, 32 * warps, smem) != cudaSuccess) return 0;
+    if (occupancy_of(&n, kfn, 32 * warps, smem) != cudaSuccess) return 0;
     return n;
 }
 
@@ -2590,11 +2642,11 @@ int quad_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt)
     if (bt) {
         auto kfn = wfa_quad_kernel<true, false>;
         if (allow_max_smem(kfn) != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
+        if (occupancy_of(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
     } else {
         auto kfn = wfa_quad_kernel<false, false>;
         if (allow_max_smem(kfn) != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
+        if (occupancy_of(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
     }
     return n;
 }
@@ -2614,7 +2666,7 @@ static int occupancy_quadg_one(int threads, size_t smem)
     auto kfn = wfa_quadg_kernel<BT, MAXT>;
     int n = 0;
     if (allow_max_smem(kfn) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess) return 0;
+    if (occupancy_of(&n, kfn, threads, smem) != cudaSuccess) return 0;
     return n;
 }
 
