@@ -185,7 +185,7 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
-    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false;
+    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false, no_band_tb = false;
     int force_period = 0;
     int arena_mb = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
@@ -301,6 +301,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->no_ckpt = env_int("WFAGPU_NO_CKPT", 0) != 0;
     d->no_bound = env_int("WFAGPU_NO_BOUND", 0) != 0;
     d->no_quad = env_int("WFAGPU_NO_QUAD", 0) != 0;
+    d->no_band_tb = env_int("WFAGPU_NO_BAND_TB", 0) != 0;
     /* two scores per barrier interval: measured equal to one (22.9 vs 22.8 ms per 8192 x 10 kbp pairs) because the deeper
      * rings cost the fifth resident CTA; opt-in */
     d->no_quad_pairs = env_int("WFAGPU_QUAD_PAIRS", 0) == 0;
@@ -429,7 +430,6 @@ static int choose_cfg(wfagpu_device *d, int x, int o, int e, int n_want, int n_m
                       bool ascii, bool bt, LaunchCfg *c)
 {
     const int A = std::max(o + e, x) + 1, E1 = e + 1, G = A;
-    const int rows = A + 2 * E1;
     const size_t smem_max = d->prop.sharedMemPerBlockOptin;        /* 227 KB on B200 */
     const size_t smem_sm = d->prop.sharedMemPerMultiprocessor;     /* 228 KB */
     const int seq_words = (int)packed_words_for(max_len);
@@ -785,19 +785,28 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
          * per thread, and small CTAs let more pairs share an SM (measured on B200, W = 512:
          * 512 threads 114 k, 256 threads 165 k, 128 threads 189 k pairs/s at 10 kbp / 5 %) */
         c.group_threads = std::min(1024, std::max(64, ((win / 4) + 31) & ~31));
+        /* packed pairs: four diagonals per thread (wfa_bandq_kernel), one quad per thread and score */
+        c.quad = !ascii && !d->no_quad;
+        /* a window spans win / 4 + 1 quads: two trips of half of them (measured on B200, W = 512, 10 kbp / 5 %:
+         * 64 threads 32.5 ms, 96 threads 31.4 ms, 128 threads 33.0 ms per 8192 pairs end to end) */
+        if (c.quad) c.group_threads = std::min(512, std::max(64, (((win / 4 + 2) / 2) + 31) & ~31));
         if (d->force_threads) c.group_threads = d->force_threads;
+        auto band_smem = [&](int stages) {
+            return c.quad ? bandq_smem_bytes(c.A, win, c.seq_words, stages) : banded_smem_bytes(c.A, win, c.seq_words, stages);
+        };
         c.stages = 2;
-        c.smem = banded_smem_bytes(c.A, win, c.seq_words, c.stages);
+        c.smem = band_smem(c.stages);
         if (c.smem > d->prop.sharedMemPerBlockOptin) {
             c.stages = 1;
-            c.smem = banded_smem_bytes(c.A, win, c.seq_words, c.stages);
+            c.smem = band_smem(c.stages);
         }
         if (c.smem > d->prop.sharedMemPerBlockOptin) {
             fprintf(stderr, "[wfagpu] band of %d diagonals does not fit in shared memory\n", win);
             return -2;
         }
         c.n_cap = n_full; c.row_stride = win; c.center = 0;
-        int occ = banded_max_ctas_per_sm(c.group_threads, c.smem, ascii, plan.with_cigar != 0);
+        int occ = c.quad ? bandq_max_ctas_per_sm(c.group_threads, c.smem, plan.with_cigar != 0)
+                         : banded_max_ctas_per_sm(c.group_threads, c.smem, ascii, plan.with_cigar != 0);
         if (occ < 1) return -1;
         c.ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ * d->prop.multiProcessorCount, n_items));
     } else {
@@ -853,13 +862,15 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     }
 
     if (!plan.with_cigar) arena_units = 0;
+    /* adaptive band on packed pairs: decision rows per pair, walked by a traceback kernel after the launch */
+    const bool band_tb = banded && c.quad && plan.with_cigar && !d->no_band_tb;
     /* keep the arenas within a third of the free device memory: fewer, not smaller, groups
      * (decision bytes: one arena per resident group; snapshots: one per pair of a sub-launch) */
     size_t items_per_launch = n_items;
     {
         const size_t budget = arena_budget;
-        if (c.ckpt) {
-            const size_t per_pair = (size_t)arena_units * sizeof(uint4) + 1;
+        if (c.ckpt || band_tb) {
+            const size_t per_pair = (size_t)arena_units * sizeof(uint4) + (band_tb ? ((size_t)d_end + 1) * sizeof(int32_t) : 0) + 1;
             items_per_launch = std::max<size_t>(1, std::min<size_t>(n_items, budget / per_pair));
             c.ctas = (int)std::min<size_t>((size_t)c.ctas, items_per_launch);
         } else {
@@ -872,11 +883,11 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     const uint64_t gring_elems = c.global_ring ? (uint64_t)(c.A + 2 * c.E1) * (uint64_t)c.row_stride : 0;
     if (s.gring.ensure(groups * gring_elems + 1)) return -1;
     const uint32_t scratch_words = plan.with_cigar ? (uint32_t)((2 * (size_t)d_end + 31) / 16 + 2) : 1;
-    const size_t arenas = c.ckpt ? items_per_launch : groups;
+    const size_t arenas = (c.ckpt || band_tb) ? items_per_launch : groups;
     if (arenas * arena_units + 1 > s.arena.cap) s.budget_cache = 0;      /* the arena grows: re-read the free memory next time */
     if (s.arena.ensure(arenas * arena_units + 1) || s.scratch.ensure(groups * scratch_words + 1)) return -1;
     const uint32_t band_lo_words = (banded && plan.with_cigar) ? (uint32_t)d_end + 1 : 0;
-    if (s.band_lo.ensure(groups * (size_t)band_lo_words + 1)) return -1;
+    if (s.band_lo.ensure((band_tb ? items_per_launch : groups) * (size_t)band_lo_words + 1)) return -1;
     /* op pool: worst case for this pass on top of what is already used */
     /* later passes run after read_counters(): the host copy of the pool head is current */
     const uint32_t pool_used = first_pass ? 0u : s.h_counters.p[CTR_POOL];
@@ -931,6 +942,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     kp.win = win;
     kp.band_lo = s.band_lo.p;
     kp.band_lo_words = band_lo_words;
+    kp.band_tb = band_tb ? 1 : 0;
     kp.gring = c.global_ring ? s.gring.p : nullptr;
     kp.gring_elems = gring_elems;
     kp.arena = s.arena.p;
@@ -983,7 +995,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         CK(cudaMemsetAsync(s.counters.p + CTR_QUEUE, 0, sizeof(uint32_t), s.stream));
         const bool time_it = first_pass && items_per_launch >= n_items && s.ev[6] && s.ev[7];
         if (time_it) CK(cudaEventRecord(s.ev[6], s.stream));
-        cudaError_t e = banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
+        cudaError_t e = (banded && c.quad) ? launch_bandq(kp, c.group_threads, c.ctas, c.smem, s.stream)
+                      : banded ? launch_banded(kp, c.group_threads, c.ctas, c.smem, ascii, s.stream)
                       : (c.quad && c.global_ring) ? launch_quadg(kp, c.group_threads, (int)std::min<size_t>(c.ctas, cnt), c.smem, s.stream)
                       : c.quad ? launch_quad(kp, c.group_threads, (int)std::min<size_t>(c.ctas, cnt), c.smem, s.stream)
                                : launch_exact(kp, c.group_threads, c.groups_per_cta, (int)std::min<size_t>(c.ctas, cnt), c.smem, ascii, s.stream);
@@ -994,6 +1007,14 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         if (time_it) { CK(cudaEventRecord(s.ev[7], s.stream)); s.wf_timed = true; }
         tr.mark("fwd");
         s.stats.launches += 1;
+        if (band_tb) {
+            e = launch_band_traceback(kp, s.stream);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "[wfagpu] band traceback kernel launch failed: %s\n", cudaGetErrorString(e));
+                return -1;
+            }
+            s.stats.launches += 1;
+        }
         if (c.ckpt) {
             /* ring snapshots -> 2-bit ops, a warp per pair */
             CK(cudaMemsetAsync(s.counters.p + CTR_TBQ, 0, sizeof(uint32_t), s.stream));

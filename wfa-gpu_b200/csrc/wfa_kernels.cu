@@ -2380,6 +2380,507 @@ int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii, bool bt)
 }
 
 /* ======================================================================== */
+/*        adaptive band, four diagonals per thread on packed int16          */
+/* ======================================================================== */
+/*
+ * Same heuristic, same results as wfa_banded_kernel, for packed (ACGT) pairs.  A ring row stores the cells of its score's
+ * window [lo, hi] at index k - base with base = lo rounded down to a multiple of four, whole quads, cells outside the window
+ * as NULL: every quad a thread reads (its own four diagonals in the rows of d - x, d - o - e, d - e and the two neighbours
+ * k - 1, k + 4) is one aligned LDS.64 / LDS.U16 whatever the windows of the source scores are -- a quad or neighbour outside
+ * the stored part of a row is a predicated-off load that leaves NULL in the register.  The recurrence runs on packed int16
+ * pairs; with backtrace the max instructions also return which operand won (VIMNMX.S16x2 with predicate outputs), which
+ * gives the decision byte of wfa_banded_kernel (bit0 I extends, bit1 D extends, bits 3:2 the winner of M: ties
+ * extend > open, D > X > I) -- four of them per 32-bit store, at byte k - base of the score's row (band_lo holds base).
+ */
+__device__ __forceinline__ uint2 lds_v2_or_null(uint32_t a, uint32_t idx, uint32_t n)
+{
+    uint2 v = make_uint2(kNull2, kNull2);
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.lt.u32 p, %3, %4;\n"
+                 "@p ld.shared.v2.u32 {%0, %1}, [%2];\n"
+                 "}\n" : "+r"(v.x), "+r"(v.y) : "r"(a), "r"(idx), "r"(n));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16_or_null(uint32_t a, uint32_t idx, uint32_t n)
+{
+    uint32_t v = kNull2 & 0xffffu;
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.lt.u32 p, %2, %3;\n"
+                 "@p ld.shared.u16 %0, [%1];\n"
+                 "}\n" : "+r"(v) : "r"(a), "r"(idx), "r"(n));
+    return v;
+}
+
+/* cells a row stores for the window [.., hi] with this base: whole quads */
+__device__ __forceinline__ uint32_t bandq_cells(int hi, int base) { return (uint32_t)(((hi - base) | 3) + 1); }
+
+struct BandQCtl {
+    uint64_t bar[2];
+    uint32_t idx[2];
+    uint32_t pos[2];
+    uint32_t n_ops;
+    uint32_t ops_off;
+    int new_center;
+    int pad;
+    unsigned long long red[32];
+};
+
+template <bool BT>
+__global__ void __launch_bounds__(512, 1) wfa_bandq_kernel(const __grid_constant__ KernelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, gsz = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = gsz >> 5;
+    const int x = p.x, e = p.e, A = p.A, W = p.win;
+    const int oe = p.o + p.e;
+    const int RW = ((W + 3) & ~3) + 8;                         /* cells per row: a window plus alignment slack */
+    const uint32_t row_bytes = ((uint32_t)RW * 2u + 15u) & ~15u;
+    const uint32_t comp_bytes = (uint32_t)A * row_bytes;
+    const uint32_t ring_bytes = 3u * comp_bytes;
+    const uint32_t win_bytes = (uint32_t)(2 * A) * 16u;             /* window records: {lo, hi, base, cells} per slot */
+    const uint32_t seq_bytes = (uint32_t)p.seq_words * 4u;
+    const uint32_t seq_total = 2u * (uint32_t)p.stages * seq_bytes;
+    const uint32_t M0 = smem_u32(smem_raw);
+    const uint32_t I0 = M0 + comp_bytes, D0 = I0 + comp_bytes;
+    const uint32_t WM = M0 + ring_bytes;                             /* M rows; the I and D rows of a slot share a window */
+    const uint32_t WG = WM + (uint32_t)A * 16u;
+    const uint32_t seq_sa = M0 + ring_bytes + win_bytes;
+    BandQCtl *ctl = reinterpret_cast<BandQCtl *>(smem_raw + ring_bytes + win_bytes + seq_total);
+
+    const uint32_t group = blockIdx.x;
+    uint32_t *const scratch = p.ops_scratch + (size_t)group * p.ops_scratch_words;
+
+    auto issue_load = [&](int stage, uint32_t idx) {
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const uint32_t pw = ((((pr.plen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        const uint32_t tw = ((((pr.tlen + 7u) >> 3) + 1u) + 3u) & ~3u;
+        unsigned char *dp = smem_raw + ring_bytes + win_bytes + (size_t)(2 * stage) * seq_bytes;
+        unsigned char *dt = dp + seq_bytes;
+        fence_proxy_async();
+        mbar_expect_tx(&ctl->bar[stage], (pw + tw) * 4u);
+        tma_load_1d(dp, p.packed + pr.p_word, pw * 4u, &ctl->bar[stage]);
+        tma_load_1d(dt, p.packed + pr.t_word, tw * 4u, &ctl->bar[stage]);
+    };
+    auto pop = [&](int slot) -> uint32_t {
+        const uint32_t pos = atomicAdd(p.queue, 1u);
+        ctl->pos[slot] = pos;
+        return pos < p.n_items ? p.order[pos] : kInvalidIdx;
+    };
+    if (tid == 0) {
+        mbar_init(&ctl->bar[0], 1);
+        mbar_init(&ctl->bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t first = pop(0);
+        ctl->idx[0] = first;
+        if (first != kInvalidIdx) issue_load(0, first);
+    }
+    __syncthreads();
+
+    int stage = 0;
+    uint32_t phase_bits = 0;
+    while (true) {
+        const uint32_t idx = ctl->idx[stage];
+        if (idx == kInvalidIdx) break;
+        if (tid == 0 && p.stages == 2) {
+            const uint32_t nxt = pop(stage ^ 1);
+            ctl->idx[stage ^ 1] = nxt;
+            if (nxt != kInvalidIdx) issue_load(stage ^ 1, nxt);
+        }
+        /* decision rows and row bases: per queue position (walked by wfa_band_traceback_kernel), else per CTA */
+        const size_t region = p.band_tb ? (size_t)ctl->pos[stage] : (size_t)group;
+        uint4 *const arena = p.arena + region * p.arena_units;
+        int32_t *const lo_tab = p.band_lo + region * p.band_lo_words;
+        const wfagpu_pair_t pr = p.pairs[idx];
+        const int plen = (int)pr.plen, tlen = (int)pr.tlen;
+        const int kt = tlen - plen;
+        const int kt_abs = kt < 0 ? -kt : kt;
+        const int tl8 = tlen - 8;
+        const uint32_t Pa = seq_sa + (uint32_t)(2 * stage) * seq_bytes;
+        const uint32_t Ta = Pa + seq_bytes;
+        const bool skip = (pr.flags & WFAGPU_PAIR_HAS_N) != 0;
+
+        /* every slot starts as the one-diagonal window [0, 0] holding NULL (aband.cu:543-578): one quad of NULLs at base 0 */
+        for (int i = tid; i < 3 * A; i += gsz) {
+            if (i < 2 * A) sts_v4(WM + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 4u));
+            sts_v2(M0 + (uint32_t)i * row_bytes, kNull2, kNull2);
+        }
+        mbar_wait(&ctl->bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        __syncthreads();
+
+        int dist = 0;
+        bool finished = false;
+        if (!skip) {
+            if (tid == 0) sts_16(M0, extend_packed(Pa, Ta, plen, tlen, 0, 0));
+            __syncthreads();
+            if (kt == 0 && lds_s16(M0) == tlen) {
+                finished = true;
+            } else {
+                int sM = 0;                                  /* ring slot of the current score: d mod A */
+                int d_rc = p.band;                           /* next score that is a multiple of `band` */
+                for (int d = 1; d < p.d_end; ++d) {
+                    const wfagpu_step_t st = p.steps[d];
+                    sM = (sM + 1 == A) ? 0 : sM + 1;
+                    if (d > d_rc) d_rc += p.band;
+                    if (st.kind == WFAGPU_STEP_NULL) continue;
+                    int sx = sM - x;  if (sx < 0) sx += A;
+                    const uint32_t aMx = M0 + (uint32_t)sx * row_bytes;
+                    const uint4 wx = lds_v4(WM + (uint32_t)sx * 16u);
+                    const int xlo = (int)wx.x, xhi = (int)wx.y, bx = (int)wx.z;
+                    const uint32_t aMc = M0 + (uint32_t)sM * row_bytes;
+                    int lo, hi, base;
+                    if (st.kind == WFAGPU_STEP_M) {
+                        lo = xlo; hi = xhi; base = bx;
+                        const int nq = ((hi - base) >> 2) + 1;
+                        for (int q = tid; q < nq; q += gsz) {
+                            const int kq = base + 4 * q;
+                            const uint32_t o2 = (uint32_t)(8 * q);
+                            const uint2 mx = lds_v2(aMx + o2);
+                            uint32_t M01 = __vadd2(mx.x, kOnes2), M23 = __vadd2(mx.y, kOnes2);
+                            if (kq < lo || kq + 3 > hi) {
+                                M01 = sel2(M01, in2(kq, lo, hi));
+                                M23 = sel2(M23, in2(kq + 2, lo, hi));
+                            }
+                            extend_quad(Pa, Ta, plen, tlen, kq, tl8, M01, M23);
+                            sts_v2(aMc + o2, M01, M23);
+                        }
+                        if (tid == 0) sts_v4(WM + (uint32_t)sM * 16u, wx);
+                    } else {
+                        int so = sM - oe; if (so < 0) so += A;
+                        int sg = sM - e;  if (sg < 0) sg += A;
+                        const uint32_t aMo = M0 + (uint32_t)so * row_bytes;
+                        const uint32_t aIe = I0 + (uint32_t)sg * row_bytes;
+                        const uint32_t aDe = D0 + (uint32_t)sg * row_bytes;
+                        const uint32_t aIc = I0 + (uint32_t)sM * row_bytes;
+                        const uint32_t aDc = D0 + (uint32_t)sM * row_bytes;
+                        const uint4 wo = lds_v4(WM + (uint32_t)so * 16u), wg = lds_v4(WG + (uint32_t)sg * 16u);
+                        const int olo = (int)wo.x, ohi = (int)wo.y, bo = (int)wo.z;
+                        const int glo = (int)wg.x, ghi = (int)wg.y, bg = (int)wg.z;
+                        const int hi_ID = max(ohi, ghi) + 1;
+                        const int lo_ID = min(olo, glo) - 1;
+                        hi = max(xhi, hi_ID);
+                        lo = min(xlo, lo_ID);
+                        const int excess = (hi - lo) - (W - 1);
+                        if (excess > 0) { hi -= (excess + 1) >> 1; lo += excess >> 1; }
+                        if ((xhi - xlo) >= W - 1 && d == d_rc) {
+                            /* first diagonal of [xlo, xhi) with the smallest distance to the target */
+                            unsigned long long best = ~0ull;
+                            for (int i = xlo + tid; i < xhi; i += gsz) {
+                                const int off = lds_s16(aMx + (uint32_t)(2 * (i - bx)));
+                                const int left_v = (int)(short)(plen - (off - i));
+                                const int left_h = (int)(short)(tlen - off);
+                                const int dt = off >= 0 ? max(left_v, left_h) : 0x7fffffff;
+                                const unsigned long long key =
+                                    ((unsigned long long)((unsigned)dt ^ 0x80000000u) << 32) | (unsigned)(i - xlo);
+                                best = key < best ? key : best;
+                            }
+                            for (int s = 16; s > 0; s >>= 1) {
+                                const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
+                                best = o < best ? o : best;
+                            }
+                            if (lane == 0) ctl->red[warp] = best;
+                            __syncthreads();
+                            if (warp == 0) {
+                                unsigned long long b = lane < nwarps ? ctl->red[lane] : ~0ull;
+                                for (int s = 16; s > 0; s >>= 1) {
+                                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, b, s);
+                                    b = o < b ? o : b;
+                                }
+                                if (lane == 0) {
+                                    int c = xlo;
+                                    if (b != ~0ull) {
+                                        const int dt = (int)((unsigned)(b >> 32) ^ 0x80000000u);
+                                        if (dt < 2 * (tlen + plen)) c = xlo + (int)(unsigned)(b & 0xffffffffu);
+                                    }
+                                    ctl->new_center = c;
+                                }
+                            }
+                            __syncthreads();
+                            lo = ctl->new_center - (W / 2);
+                            hi = lo + W - 1;
+                        }
+                        base = lo & ~3;
+                        /* nobody reads the window of the slot being rewritten during this score (it is
+                         * never one of its own sources: x, o+e, e < A), so it can be updated right away */
+                        if (tid == 0) {
+                            const uint4 w = make_uint4((uint32_t)lo, (uint32_t)hi, (uint32_t)base, bandq_cells(hi, base));
+                            sts_v4(WM + (uint32_t)sM * 16u, w);
+                            sts_v4(WG + (uint32_t)sM * 16u, w);
+                            if (BT) lo_tab[d] = base;
+                        }
+                        uint8_t *const rowb = reinterpret_cast<uint8_t *>(arena + st.row_off);
+                        const uint32_t nx = wx.w, no = wo.w, ng = wg.w;
+                        const int nq = ((hi - base) >> 2) + 1;
+                        for (int q = tid; q < nq; q += gsz) {
+                            const int kq = base + 4 * q;
+                            const uint32_t o2 = (uint32_t)(8 * q);
+                            const int jo = kq - bo, jg = kq - bg, jx = kq - bx;
+                            const uint32_t ao = aMo + (uint32_t)(2 * jo), ai = aIe + (uint32_t)(2 * jg), ad = aDe + (uint32_t)(2 * jg);
+                            const uint2 mo = lds_v2_or_null(ao, (uint32_t)jo, no);
+                            const uint32_t ml = lds_u16_or_null(ao - 2u, (uint32_t)(jo - 1), no);
+                            const uint32_t mr = lds_u16_or_null(ao + 8u, (uint32_t)(jo + 4), no);
+                            const uint2 ie = lds_v2_or_null(ai, (uint32_t)jg, ng);
+                            const uint32_t il = lds_u16_or_null(ai - 2u, (uint32_t)(jg - 1), ng);
+                            const uint2 de = lds_v2_or_null(ad, (uint32_t)jg, ng);
+                            const uint32_t dr = lds_u16_or_null(ad + 8u, (uint32_t)(jg + 4), ng);
+                            const uint2 mx = lds_v2_or_null(aMx + (uint32_t)(2 * jx), (uint32_t)jx, nx);
+                            const uint32_t oL01 = __byte_perm(ml, mo.x, 0x5410);          /* Mo (k-1 | k)   */
+                            const uint32_t oMid = __byte_perm(mo.x, mo.y, 0x5432);        /* Mo (k+1 | k+2) */
+                            const uint32_t oR23 = __byte_perm(mo.y, mr, 0x5432);          /* Mo (k+3 | k+4) */
+                            const uint32_t eI01 = __byte_perm(il, ie.x, 0x5410), eI23 = __byte_perm(ie.x, ie.y, 0x5432);
+                            const uint32_t eD01 = __byte_perm(de.x, de.y, 0x5432), eD23 = __byte_perm(de.y, dr, 0x5432);
+                            const uint32_t X01 = __vadd2(mx.x, kOnes2), X23 = __vadd2(mx.y, kOnes2);
+                            uint32_t I01, I23, D01, D23, M01, M23, dec = 0;
+                            if (BT) {
+                                bool i0, i1, i2, i3, d0, d1, d2, d3, a0, a1, a2, a3, b0, b1, b2, b3;
+                                I01 = __vadd2(__vibmax_s16x2(eI01, oL01, &i1, &i0), kOnes2);      /* pred: extend >= open */
+                                I23 = __vadd2(__vibmax_s16x2(eI23, oMid, &i3, &i2), kOnes2);
+                                D01 = __vibmax_s16x2(eD01, oMid, &d1, &d0);
+                                D23 = __vibmax_s16x2(eD23, oR23, &d3, &d2);
+                                const uint32_t T01 = __vibmax_s16x2(D01, X01, &a1, &a0);          /* pred: D >= X */
+                                const uint32_t T23 = __vibmax_s16x2(D23, X23, &a3, &a2);
+                                M01 = __vibmax_s16x2(T01, I01, &b1, &b0);                          /* pred: max(D, X) >= I */
+                                M23 = __vibmax_s16x2(T23, I23, &b3, &b2);
+                                dec = ((i0 ? 1u : 0u) + (d0 ? 2u : 0u) + (b0 ? (a0 ? 12u : 8u) : 4u)) +
+                                      ((i1 ? 1u : 0u) + (d1 ? 2u : 0u) + (b1 ? (a1 ? 12u : 8u) : 4u)) * 0x100u +
+                                      ((i2 ? 1u : 0u) + (d2 ? 2u : 0u) + (b2 ? (a2 ? 12u : 8u) : 4u)) * 0x10000u +
+                                      ((i3 ? 1u : 0u) + (d3 ? 2u : 0u) + (b3 ? (a3 ? 12u : 8u) : 4u)) * 0x1000000u;
+                            } else {
+                                I01 = __vadd2(__vmaxs2(eI01, oL01), kOnes2);
+                                I23 = __vadd2(__vmaxs2(eI23, oMid), kOnes2);
+                                D01 = __vmaxs2(eD01, oMid);
+                                D23 = __vmaxs2(eD23, oR23);
+                                M01 = __vimax3_s16x2(X01, D01, I01);
+                                M23 = __vimax3_s16x2(X23, D23, I23);
+                            }
+                            if (kq < lo || kq + 3 > hi) {
+                                /* quad straddles the window: stores outside [lo, hi] are dropped, i.e. read back as NULL */
+                                const uint32_t k01 = in2(kq, lo, hi), k23 = in2(kq + 2, lo, hi);
+                                I01 = sel2(I01, k01); D01 = sel2(D01, k01); M01 = sel2(M01, k01);
+                                I23 = sel2(I23, k23); D23 = sel2(D23, k23); M23 = sel2(M23, k23);
+                            }
+                            sts_v2(aIc + o2, I01, I23);
+                            sts_v2(aDc + o2, D01, D23);
+                            if (BT) *reinterpret_cast<uint32_t *>(rowb + 4 * q) = dec;
+                            extend_quad(Pa, Ta, plen, tlen, kq, tl8, M01, M23);
+                            sts_v2(aMc + o2, M01, M23);
+                        }
+                    }
+                    __syncthreads();
+                    if (kt_abs <= d) {
+                        const int t = (kt >= lo && kt <= hi) ? lds_s16(aMc + (uint32_t)(2 * (kt - base))) : kOffNull;
+                        if (t == tlen) { finished = true; dist = d; break; }
+                        if (t > tlen) break;                 /* aband.cu:678-681 */
+                    }
+                }
+            }
+        }
+
+        /* ---- traceback: as in wfa_banded_kernel; lo_tab holds the base of every score's row ---- */
+        if (tid == 0) {
+            uint32_t n_ops = 0, ops_off = 0;
+            if (BT && finished && dist > 0 && !p.band_tb) {
+                int cd = dist, ck = kt, comp = 0;
+                uint32_t word = 0;
+                bool bad = false;
+                auto resolveM = [&](int dd) { while (dd > 0 && p.steps[dd].kind == WFAGPU_STEP_NULL) dd -= A; return dd; };
+                auto resolveG = [&](int dd) { while (dd > 0 && p.steps[dd].kind != WFAGPU_STEP_MDI) dd -= A; return dd; };
+                while (!(comp == 0 && cd == 0)) {
+                    if (cd < 0) { bad = true; break; }
+                    const wfagpu_step_t st = p.steps[cd];
+                    uint32_t op;
+                    if (comp == 0 && st.kind == WFAGPU_STEP_M) {
+                        op = OP_SUB;
+                        cd = resolveM(cd - x);
+                    } else {
+                        if (st.kind != WFAGPU_STEP_MDI) { bad = true; break; }
+                        const int ii = ck - lo_tab[cd];
+                        if (ii < 0 || ii >= RW) { bad = true; break; }
+                        const uint32_t dec = reinterpret_cast<const uint8_t *>(arena + st.row_off)[ii];
+                        if (comp == 0) {
+                            op = OP_SUB;
+                            const int mop = (int)(dec >> 2) & 3;
+                            if (mop == OP_SUB) cd = resolveM(cd - x);
+                            else if (mop == OP_INS) comp = 1;
+                            else comp = 2;
+                        } else if (comp == 1) {
+                            op = OP_INS;
+                            ck -= 1;
+                            if (dec & 1u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+                        } else {
+                            op = OP_DEL;
+                            ck += 1;
+                            if (dec & 2u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+                        }
+                    }
+                    word |= op << (2 * (n_ops & 15u));
+                    ++n_ops;
+                    if ((n_ops & 15u) == 0) { scratch[(n_ops >> 4) - 1] = word; word = 0; }
+                    if ((n_ops >> 4) >= p.ops_scratch_words) { bad = true; break; }
+                }
+                if (bad) { n_ops = 0; finished = false; }
+                if (n_ops & 15u) scratch[n_ops >> 4] = word;
+                const uint32_t nw = (n_ops + 15u) >> 4;
+                ops_off = atomicAdd(p.ops_pool_head, nw);
+                if (ops_off + nw > p.ops_pool_words) { n_ops = 0; finished = false; }
+            }
+            ctl->n_ops = n_ops;
+            ctl->ops_off = ops_off;
+            wfagpu_pair_out_t r;
+            r.distance = finished ? dist : 0;
+            r.ops_off = ops_off;
+            r.n_ops = n_ops;
+            if (skip) {
+                r.status = WFAGPU_ST_NEEDS_ASCII;
+                p.ascii_list[atomicAdd(p.ascii_count, 1u)] = idx;
+            } else if (finished) {
+                r.status = WFAGPU_ST_FINISHED;
+            } else {
+                r.status = WFAGPU_ST_OVERBUDGET;
+                p.retry_list[atomicAdd(p.retry_count, 1u)] = idx;
+            }
+            p.out[idx] = r;
+        }
+        __syncthreads();
+        if (BT) {
+            const uint32_t nw = (ctl->n_ops + 15u) >> 4;
+            const uint32_t off = ctl->ops_off;
+            for (uint32_t i = tid; i < nw; i += gsz) p.ops_pool[off + i] = scratch[i];
+        }
+        __syncthreads();
+        if (p.stages == 2) {
+            stage ^= 1;
+        } else {
+            if (tid == 0) {
+                const uint32_t nxt = pop(0);
+                ctl->idx[0] = nxt;
+                if (nxt != kInvalidIdx) issue_load(0, nxt);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+/* The backtrace of wfa_bandq_kernel's decision bytes, one thread per pair of the launch: a walk of dependent loads (the
+ * score's row base, then the byte), so thousands of them in flight beat one walk per CTA while its other threads wait
+ * (17 % of the warp time of the fused version).  Ops oldest-last, 16 per word, straight into the pool. */
+__global__ void __launch_bounds__(128) wfa_band_traceback_kernel(const __grid_constant__ KernelParams p)
+{
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= p.n_items) return;
+    const uint32_t idx = p.order[pos];
+    wfagpu_pair_out_t res = p.out[idx];
+    if (!(res.status & WFAGPU_ST_FINISHED) || res.distance <= 0) return;
+    const int x = p.x, e = p.e, A = p.A, oe = p.o + p.e;
+    const int RW = ((p.win + 3) & ~3) + 8;
+    const wfagpu_pair_t pr = p.pairs[idx];
+    const uint4 *const arena = p.arena + (size_t)pos * p.arena_units;
+    const int32_t *const lo_tab = p.band_lo + (size_t)pos * p.band_lo_words;
+    const int dist = res.distance;
+    const uint32_t nw_max = ((2u * (uint32_t)dist + 15u) >> 4) + 1u;       /* at most 2 ops per score */
+    const uint32_t ops_off = atomicAdd(p.ops_pool_head, nw_max);
+    bool bad = ops_off + nw_max > p.ops_pool_words;
+    uint32_t *const ops = p.ops_pool + ops_off;
+    int cd = dist, ck = (int)pr.tlen - (int)pr.plen, comp = 0;
+    uint32_t word = 0, n_ops = 0;
+    auto resolveM = [&](int dd) { while (dd > 0 && p.steps[dd].kind == WFAGPU_STEP_NULL) dd -= A; return dd; };
+    auto resolveG = [&](int dd) { while (dd > 0 && p.steps[dd].kind != WFAGPU_STEP_MDI) dd -= A; return dd; };
+    while (!bad && !(comp == 0 && cd == 0)) {
+        if (cd < 0) { bad = true; break; }
+        const wfagpu_step_t st = p.steps[cd];
+        uint32_t op;
+        if (comp == 0 && st.kind == WFAGPU_STEP_M) {
+            op = OP_SUB;
+            cd = resolveM(cd - x);
+        } else {
+            if (st.kind != WFAGPU_STEP_MDI) { bad = true; break; }
+            const int ii = ck - lo_tab[cd];
+            if (ii < 0 || ii >= RW) { bad = true; break; }
+            const uint32_t dec = reinterpret_cast<const uint8_t *>(arena + st.row_off)[ii];
+            if (comp == 0) {
+                op = OP_SUB;
+                const int mop = (int)(dec >> 2) & 3;
+                if (mop == OP_SUB) cd = resolveM(cd - x);
+                else if (mop == OP_INS) comp = 1;
+                else comp = 2;
+            } else if (comp == 1) {
+                op = OP_INS;
+                ck -= 1;
+                if (dec & 1u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+            } else {
+                op = OP_DEL;
+                ck += 1;
+                if (dec & 2u) cd = resolveG(cd - e); else { cd = resolveM(cd - oe); comp = 0; }
+            }
+        }
+        word |= op << (2 * (n_ops & 15u));
+        ++n_ops;
+        if ((n_ops & 15u) == 0) { ops[(n_ops >> 4) - 1] = word; word = 0; }
+        if (n_ops >= 16u * nw_max) { bad = true; break; }                  /* never: at most 2 ops per score */
+    }
+    if (bad) {
+        /* cannot happen for a finished pair; handled like a pair that ran out of budget */
+        res.status = WFAGPU_ST_OVERBUDGET;
+        res.distance = 0;
+        res.ops_off = 0;
+        res.n_ops = 0;
+        p.retry_list[atomicAdd(p.retry_count, 1u)] = idx;
+    } else {
+        if (n_ops & 15u) ops[n_ops >> 4] = word;
+        res.ops_off = ops_off;
+        res.n_ops = n_ops;
+    }
+    p.out[idx] = res;
+}
+
+cudaError_t launch_band_traceback(const KernelParams &p, cudaStream_t s)
+{
+    if (p.n_items == 0) return cudaSuccess;
+    wfa_band_traceback_kernel<<<(p.n_items + 127u) / 128u, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+size_t bandq_smem_bytes(int A, int win, int seq_words, int stages)
+{
+    const size_t rw = (size_t)((win + 3) & ~3) + 8;
+    const size_t row_bytes = (rw * 2 + 15) & ~(size_t)15;
+    const size_t ring_bytes = 3 * (size_t)A * row_bytes;
+    const size_t win_bytes = 2 * (size_t)A * 16;
+    return ring_bytes + win_bytes + 2 * (size_t)stages * seq_words * 4 + sizeof(BandQCtl) + 16;
+}
+
+cudaError_t launch_bandq(const KernelParams &p, int threads, int ctas, size_t smem_bytes, cudaStream_t s)
+{
+    cudaError_t err;
+    if (p.with_bt) {
+        auto kfn = wfa_bandq_kernel<true>;
+        if ((err = allow_max_smem(kfn)) != cudaSuccess) return err;
+        kfn<<<ctas, threads, smem_bytes, s>>>(p);
+    } else {
+        auto kfn = wfa_bandq_kernel<false>;
+        if ((err = allow_max_smem(kfn)) != cudaSuccess) return err;
+        kfn<<<ctas, threads, smem_bytes, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+int bandq_max_ctas_per_sm(int threads, size_t smem_bytes, bool bt)
+{
+    int n = 0;
+    if (bt) {
+        auto kfn = wfa_bandq_kernel<true>;
+        if (allow_max_smem(kfn) != cudaSuccess) return 0;
+        if (occupancy_of(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
+    } else {
+        auto kfn = wfa_bandq_kernel<false>;
+        if (allow_max_smem(kfn) != cudaSuccess) return 0;
+        if (occupancy_of(&n, kfn, threads, smem_bytes) != cudaSuccess) return 0;
+    }
+    return n;
+}
+
+/* ======================================================================== */
 /*                       CIGAR text emission on the device                  */
 /* ======================================================================== */
 /*

@@ -16,6 +16,7 @@
  *                        the path, one warp per pair (replaces the bt-word/offload chain of
  *                        sequence_alignment_kernel.cu and the gather in lib/align.cu)
  *   wfa_banded_kernel    adaptive band (-B), the reference's heuristic bit for bit
+ *   wfa_bandq_kernel     the same, four diagonals per thread on packed int16 (packed pairs)
  *   cigar_text_kernel    op stream + sequences -> CIGAR text on the device (utils/cigar.c)
  *
  * Semantics reproduced from the reference:
@@ -61,6 +62,8 @@ struct KernelParams {
     int win;                      /* banded kernel: window width in diagonals               */
     int32_t *band_lo;             /* banded kernel: per group, lo of every score (traceback) */
     uint32_t band_lo_words;
+    int band_tb;                  /* wfa_bandq_kernel: arena and band_lo are per queue position and the backtrace is walked
+                                   * by wfa_band_traceback_kernel (a thread per pair) after the launch */
     int stages;                   /* 1 or 2 sequence buffers per group (2 = prefetch next pair) */
     int quad_pairs;               /* quad kernel: two scores per barrier (needs ring_m = A + 1, ring_g = E1 + 1) */
     int ring_m, ring_g;           /* quad kernel: rows of the M ring and of the I / D rings */
@@ -135,6 +138,12 @@ cudaError_t launch_banded(const KernelParams &p, int threads, int ctas, size_t s
                           cudaStream_t s);
 size_t banded_smem_bytes(int A, int win, int seq_words, int stages);
 int banded_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii_extend, bool with_bt);
+/* the same heuristic, four diagonals per thread on packed int16 (packed pairs only) */
+cudaError_t launch_bandq(const KernelParams &p, int threads, int ctas, size_t smem_bytes, cudaStream_t s);
+size_t bandq_smem_bytes(int A, int win, int seq_words, int stages);
+int bandq_max_ctas_per_sm(int threads, size_t smem_bytes, bool with_bt);
+/* decision bytes of wfa_bandq_kernel -> 2-bit ops, one thread per pair of the launch */
+cudaError_t launch_band_traceback(const KernelParams &p, cudaStream_t s);
 int large_max_ctas_per_sm(int threads, size_t smem_bytes, bool ascii_extend, bool with_bt);
 int exact_max_ctas_per_sm(int group_threads, int groups_per_cta, size_t smem_bytes, bool ascii_extend, bool with_bt,
                           bool ckpt = false);

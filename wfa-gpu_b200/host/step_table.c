@@ -22,8 +22,9 @@ int wfagpu_build_step_table(int x, int o, int e, int max_steps, int max_dist, in
     int steps = 1; /* the reference counts the score-0 wavefront as step 1 (kernel.cu:580-581) */
     int n = 0;     /* half width of the computed diagonal range                                  */
     int mdi = 0;   /* number of M/I/D steps so far (the reference's wavefront growth)            */
-    /* one decision byte per cell, rows padded to 16-byte units */
-    const uint64_t band_units = banded_win > 0 ? (uint64_t)((banded_win + 15) / 16) : 0;
+    /* one decision byte per cell, rows padded to 16-byte units; a banded row starts at the window's first diagonal rounded
+     * down to a multiple of four (wfa_bandq_kernel) and holds whole quads: up to win + 6 bytes */
+    const uint64_t band_units = banded_win > 0 ? (uint64_t)((banded_win + 8 + 15) / 16) : 0;
     int d;
     has_m[0] = 1;
     if (tab) { tab[0].row_off = 0; tab[0].n = 0; tab[0].kind = WFAGPU_STEP_M; }
