@@ -27,4 +27,24 @@ for pen, cigar in (((2, 3, 1), True), ((2, 3, 1), False), ((5, 3, 2), True), ((4
         bad = check_against_oracle(O, a, *pen, 400, cigar, big_budget=12000)
         print(pen, cigar, rep, "mismatches", len(bad), bad[:3], a.run_stats())
         bad_total += len(bad)
+# adaptive band (packed pairs: wfa_bandq_kernel + wfa_band_traceback_kernel; WFAGPU_NO_BAND_TB=1: backtrace inside the kernel;
+# WFAGPU_NO_QUAD=1: wfa_banded_kernel, one diagonal per thread): every pair the band finishes equals the oracle's banded result
+for pen, cigar, band, window, specs in (((2, 3, 1), True, 10, 64, [(120, 1000, 0.03, 0.10)]), ((2, 3, 1), True, 25, 512, [(12, 6000, 0.04, 0.06)]),
+                                        ((4, 6, 2), True, 25, 128, [(60, 1500, 0.05, 0.08)]), ((2, 3, 1), False, 5, 96, [(100, 800, 0.05, 0.05)])):
+    a = synth_aligner(specs, 0xB2005100 + band)
+    a.add_sequences("ACGT" * 200, "ACGT" * 200 + "T" * 90)
+    assert a.initialize_parameters(*pen)
+    a.options.compute_cigar = cigar
+    a.options.max_error = 2000
+    a.options.band = band
+    a.options.threads_per_block = window
+    a.align()
+    bad = 0
+    for i in range(a.num_pairs):
+        pp, tt = a.pair(i)
+        r = O.align(pp, tt, *pen, 2000, band=band, window=window, cigar=cigar)
+        if r["finished"]:
+            bad += (a.error(i) != r["distance"]) or (cigar and a.cigar(i) != r["cigar"])
+    print("banded", pen, cigar, band, window, "mismatches", bad, a.run_stats())
+    bad_total += bad
 sys.exit(1 if bad_total else 0)

@@ -20,7 +20,9 @@ FAMILIES = {
     "warp":       (192, 150, 0.04, 50, True, -1, 0, {}),
     "cta":        (40, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_QUAD_MIN": "1"}),
     "score":      (40, 1000, 0.10, 400, False, -1, 0, {"WFAGPU_QUAD_MIN": "1"}),
-    "banded":     (24, 2000, 0.05, 400, True, 10, 128, {}),
+    "banded":     (24, 2000, 0.05, 400, True, 10, 128, {}),                            # wfa_bandq_kernel + wfa_band_traceback_kernel
+    "banded_one": (24, 2000, 0.05, 400, True, 10, 128, {"WFAGPU_NO_QUAD": "1"}),       # wfa_banded_kernel (one diagonal per thread)
+    "banded_fused": (24, 2000, 0.05, 400, True, 10, 128, {"WFAGPU_NO_BAND_TB": "1"}),  # wfa_bandq_kernel, backtrace inside
     "large":      (12, 600, 0.08, 200, True, -1, 0, {"WFAGPU_FORCE_LARGE": "1"}),
     "ascii":      (24, 400, 0.05, 100, True, -1, 0, {}),
     "redispatch": (32, 800, 0.10, 40, True, -1, 0, {}),
