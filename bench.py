@@ -400,7 +400,7 @@ def envelope_block(wfagpu, a, local):
         "for _ in range(3):\n"
         "    a.reset_results(); t0=time.perf_counter(); a.align(); ts.append(time.perf_counter()-t0)\n"
         "print(json.dumps({'ts':ts,'st':a.run_stats()}))\n") % (os.path.join(ROOT, "wfa-gpu_b200", "python"), SEED, PAIRS_PER_GPU, LENGTH, ERR, ERR, MAX_ERROR)
-    for key, env in (("fresh_process", {}), ("no_hint", {"WFAGPU_NO_HINT": "1"})):
+    for key, env in (("fresh_process", {}), ("no_hint", {"WFAGPU_NO_HINT": "1"}), ("no_hint_no_prebound", {"WFAGPU_NO_HINT": "1", "WFAGPU_NO_PREBOUND": "1"})):
         try:
             pr = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)), **env),
                                 capture_output=True, text=True, timeout=600)
@@ -409,8 +409,11 @@ def envelope_block(wfagpu, a, local):
                         "call_3_alignments_per_s": round(PAIRS_PER_GPU / r["ts"][2], 1), "redispatched_last_call": int(r["st"]["redispatched"])}
         except Exception as e:                                                  # pragma: no cover
             out[key] = {"error": str(e)[:200]}
-    out["fresh_process"]["note"] = "call 1 = cold (CUDA context, buffer allocation, rings sized for -e 3000); calls 2+ provisioned from the previous call"
-    out["no_hint"]["note"] = "WFAGPU_NO_HINT=1: every call provisions its rings for the full -e 3000 budget"
+    out["fresh_process"]["note"] = ("call 1 = cold (CUDA context, buffer allocation); every call sizes its rings from the score bounds of its own "
+                                    "pairs (bound kernel first, one host round trip per chunk)")
+    out["no_hint"]["note"] = "WFAGPU_NO_HINT=1: nothing remembered between calls; the rings still follow the batch's own score bounds"
+    out["no_hint_no_prebound"]["note"] = ("WFAGPU_NO_HINT=1 WFAGPU_NO_PREBOUND=1: the policy before bound-first provisioning -- rings for the full "
+                                          "-e 3000 budget, one resident CTA less per SM")
     # (2) stale hint: a 2 % batch teaches the library small scores, then the 5 % batch arrives
     low = make_aligner(wfagpu, SEED + 1, PAIRS_PER_GPU, LENGTH, 0.02, 0.02, PEN, max_error=MAX_ERROR, cigar=True)
     low.align()
@@ -420,8 +423,21 @@ def envelope_block(wfagpu, a, local):
     dt = time.perf_counter() - t0
     st = a.run_stats()
     out["stale_hint"] = {"alignments_per_s": round(a.num_pairs / dt, 1), "redispatched": int(st["redispatched"]),
-                         "note": "the headline 5 % batch right after a 2 % batch (rings provisioned for scores ~650): every chunk's first pass is "
-                                 "too small and its pairs are re-dispatched on the GPU; the next call is provisioned correctly again"}
+                         "note": "the headline 5 % batch right after a 2 % batch (the remembered scores are ~650): the rings follow the bounds of "
+                                 "the batch itself, nothing is re-dispatched"}
+    # the other direction: the 2 % batch right after the 5 % batch, against its own steady state
+    low.reset_results()
+    t0 = time.perf_counter()
+    low.align()
+    dt_after = time.perf_counter() - t0
+    low.reset_results()
+    t0 = time.perf_counter()
+    low.align()
+    dt_steady = time.perf_counter() - t0
+    out["stale_hint_high"] = {"alignments_per_s": round(low.num_pairs / dt_after, 1), "steady_alignments_per_s": round(low.num_pairs / dt_steady, 1),
+                              "redispatched": int(low.run_stats()["redispatched"]),
+                              "note": "a 2 % batch right after the 5 % batch (remembered scores ~1600: where bounding every pair does not pay, a "
+                                      "128-pair sample of bounds detects the stale memory) next to the same call repeated"}
     low.destroy()
     a.reset_results()
     a.align()                                                                    # leave the hint as the headline batch wants it
@@ -616,7 +632,7 @@ def run_ours(args):
                        "(page-locked by wfagpu_initialize_aligner; H2D, kernels, CIGAR text printed on the GPU, D2H, copy into results[i])"},
         "gpu_launches": int(launches_per_step * args.steps),
         "pending_after_timed_pass": int(pending),
-        "hint_note": "rings of a step are provisioned from the previous step's largest score (here the identical batch); see envelope for cold / un-hinted / stale-hint numbers",
+        "hint_note": "rings of a step are sized from the score bounds of its own pairs (bound kernel first); what earlier calls needed only decides whether bounding pays and the first-pass budget beyond -e; see envelope for cold / un-hinted / stale-memory numbers",
         "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "per_rank": per_rank,
     }
     if e2e_inlib:

@@ -124,6 +124,7 @@ struct Slot {
     bool wf_timed = false;             /* ev[6], ev[7] bracket the first pass's wavefront kernel */
     cudaEvent_t ev_tab = nullptr;      /* after the last upload of a host-built table (step table, snapshot offsets) */
     bool tab_inflight = false;
+    std::vector<int32_t> bound_sorted; /* scratch of the bound-first provisioning */
     int first_steps = 0;               /* wavefront-step budget the first pass of this batch ran with (>= plan.max_steps) */
     DevBuf<char> ascii;
     DevBuf<uint32_t> packed;
@@ -185,7 +186,7 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
-    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false, no_band_tb = false;
+    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false, no_band_tb = false, no_prebound = false;
     int force_period = 0;
     int arena_mb = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
@@ -302,6 +303,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->no_bound = env_int("WFAGPU_NO_BOUND", 0) != 0;
     d->no_quad = env_int("WFAGPU_NO_QUAD", 0) != 0;
     d->no_band_tb = env_int("WFAGPU_NO_BAND_TB", 0) != 0;
+    d->no_prebound = env_int("WFAGPU_NO_PREBOUND", 0) != 0;
     /* two scores per barrier interval: measured equal to one (22.9 vs 22.8 ms per 8192 x 10 kbp pairs) because the deeper
      * rings cost the fifth resident CTA; opt-in */
     d->no_quad_pairs = env_int("WFAGPU_QUAD_PAIRS", 0) == 0;
@@ -750,6 +752,61 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
         if (cap < d_reach) d_reach = (int)std::max<long long>(cap, 2);
         if (d_reach < d_want) d_want = d_reach;
     }
+    /* Packed exact first pass where the per-pair score bounds pay (long reads): the bound kernel runs first and its
+     * largest bound sizes the rings -- what this batch needs, not what the last one needed, so a first call, a call
+     * without hints and a call after a batch of another kind all run at the speed of a well-hinted one.  Costs one
+     * host round trip per pass (bounds back: 4 bytes per pair). */
+    int d_p99 = 0;                           /* 99 % of the bounded pairs finish below this score (0 = unknown) */
+    if (first_pass && !have_bounds && plan.band <= 0 && !ascii && !d->no_bound && !d->no_prebound && n_items == s.n) {
+        bool pays = d->force_bound;
+        if (!pays) {
+            const bool h = d_want < d_full && d->hint_mean > 0 && d->hint_dist > 0;
+            const double m = h ? d->hint_mean : 0.5 * (d_want - 1);
+            const double r = std::min(2.0, std::max(1.0, (d_want - 1) / std::max(1.0, m)));
+            const double cells = r * r / 4 + (1.5 * r - 1) * (1 - r / 2);
+            pays = (cells - 0.5) * m > 130.0;
+        }
+        if (!pays && d_want < d_full && d->hint_dist > 0 && s.max_len >= 2000 && n_items >= 1024 && order_dev == s.order.p) {
+            /* a hint tight enough that bounding every pair does not pay: is it still true for this batch?  Bound the first
+             * 128 pairs of the queue; if they already outgrow the hint (every pair would be re-dispatched) or stay far
+             * below it (rings wider than needed), provision from this batch's own bounds after all */
+            constexpr size_t kSample = 128;
+            int rcb = run_bound_only(d, s, plan, max_steps, order_dev, kSample);
+            if (rcb) return rcb;
+            if (s.h_bound.ensure(s.n + 1)) return -1;
+            CK(cudaMemcpyAsync(s.h_bound.p, s.bound.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            long long smax = 0;
+            for (size_t i = 0; i < kSample; ++i) {
+                const uint32_t idx = s.h_order.p[i];
+                if (idx < s.n) smax = std::max<long long>(smax, std::min<int32_t>(s.h_bound.p[idx], d_full));
+            }
+            const long long covered = (long long)d->hint_dist + (long long)d->hint_dist * d->hint_min_pm / 1000;
+            pays = smax > covered || smax * 13 < (long long)d->hint_dist * 10;
+        }
+        if (pays) {
+            int rcb = run_bound_only(d, s, plan, max_steps, order_dev, n_items);
+            if (rcb) return rcb;
+            if (s.h_bound.ensure(s.n + 1)) return -1;
+            CK(cudaMemcpyAsync(s.h_bound.p, s.bound.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            std::vector<int32_t> &bv = s.bound_sorted;
+            bv.clear();
+            for (size_t i = 0; i < s.n; ++i)
+                if (s.h_bound.p[i] < d_full - 1) bv.push_back(s.h_bound.p[i]);
+            have_bounds = true;
+            if (!bv.empty()) {
+                const size_t k99 = (bv.size() - 1) - (bv.size() - 1) / 100;
+                std::nth_element(bv.begin(), bv.begin() + (long)k99, bv.end());
+                const int b99 = bv[k99];
+                const int bmax = *std::max_element(bv.begin() + (long)k99, bv.end());
+                d_want = std::min(d_full, bmax + 2);
+                d_want = std::min(d_want, d_reach);
+                d_p99 = std::min(d_want, b99 + 2);
+                hinted = false;
+            }
+        }
+    }
     const int pen_e = plan.e;
     const long long kt_max = s.kt_max;
     auto n_need = [&](int d_end) -> int {
@@ -771,6 +828,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     int n_min = n_want;
     if (hinted && plan.band <= 0)
         n_min = std::min(n_want, n_need((int)std::min<long long>((long long)d->hint_dist + (long long)d->hint_dist * d->hint_min_pm / 1000 + 4, d_full - 1) + 1));
+    if (d_p99 > 0) n_min = std::min(n_want, n_need(d_p99));      /* rings for 99 % of the pairs when that buys a resident CTA */
     const bool banded = plan.band > 0;
     LaunchCfg c{};
     int rc = 0;
