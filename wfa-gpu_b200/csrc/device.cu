@@ -125,6 +125,7 @@ struct Slot {
     cudaEvent_t ev_tab = nullptr;      /* after the last upload of a host-built table (step table, snapshot offsets) */
     bool tab_inflight = false;
     std::vector<int32_t> bound_sorted; /* scratch of the bound-first provisioning */
+    std::vector<uint32_t> bound_count;
     int first_steps = 0;               /* wavefront-step budget the first pass of this batch ran with (>= plan.max_steps) */
     DevBuf<char> ascii;
     DevBuf<uint32_t> packed;
@@ -186,7 +187,7 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
-    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false, no_band_tb = false, no_prebound = false;
+    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false, no_band_tb = false, no_prebound = false, no_bound_order = false;
     int force_period = 0;
     int arena_mb = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
@@ -304,6 +305,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->no_quad = env_int("WFAGPU_NO_QUAD", 0) != 0;
     d->no_band_tb = env_int("WFAGPU_NO_BAND_TB", 0) != 0;
     d->no_prebound = env_int("WFAGPU_NO_PREBOUND", 0) != 0;
+    d->no_bound_order = env_int("WFAGPU_NO_BOUND_ORDER", 0) != 0;
     /* two scores per barrier interval: measured equal to one (22.9 vs 22.8 ms per 8192 x 10 kbp pairs) because the deeper
      * rings cost the fifth resident CTA; opt-in */
     d->no_quad_pairs = env_int("WFAGPU_QUAD_PAIRS", 0) == 0;
@@ -795,6 +797,20 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
             for (size_t i = 0; i < s.n; ++i)
                 if (s.h_bound.p[i] < d_full - 1) bv.push_back(s.h_bound.p[i]);
             have_bounds = true;
+            if (order_dev == s.order.p && !d->no_bound_order) {
+                /* longest first by the pair's own bound (work ~ bound^2): the queue's tail is made of the cheapest pairs
+                 * (counting sort, descending; pairs without a bound first).  The order list was uploaded before the sync. */
+                std::vector<uint32_t> &cnt = s.bound_count;
+                cnt.assign((size_t)d_full + 1, 0u);
+                for (size_t i = 0; i < s.n; ++i) cnt[(size_t)std::min(std::max(s.h_bound.p[i], 0), d_full - 1)] += 1;
+                uint32_t acc = 0;
+                for (int b = d_full - 1; b >= 0; --b) { const uint32_t c0 = cnt[(size_t)b]; cnt[(size_t)b] = acc; acc += c0; }
+                for (size_t i = 0; i < s.n; ++i) {
+                    const size_t b = (size_t)std::min(std::max(s.h_bound.p[i], 0), d_full - 1);
+                    s.h_order.p[cnt[b]++] = (uint32_t)i;
+                }
+                CK(cudaMemcpyAsync(s.order.p, s.h_order.p, s.n * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            }
             if (!bv.empty()) {
                 const size_t k99 = (bv.size() - 1) - (bv.size() - 1) / 100;
                 std::nth_element(bv.begin(), bv.begin() + (long)k99, bv.end());
