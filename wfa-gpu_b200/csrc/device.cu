@@ -156,6 +156,7 @@ struct Slot {
     int ck_key[1] = {-1};              /* period the offsets were built for */
     PinBuf<wfagpu_pair_t> h_pairs;
     PinBuf<uint32_t> h_order;
+    PinBuf<uint32_t> h_seed;           /* one word: the re-dispatch counter a first pass starts from */
     PinBuf<wfagpu_pair_out_t> h_out;
     PinBuf<uint32_t> h_pool;
     PinBuf<uint32_t> h_counters;
@@ -187,7 +188,7 @@ struct wfagpu_device {
     Slot slots[2];
     bool count_cells = false;
     int force_threads = 0, force_stages = 0, force_ctas_per_sm = 0, force_warp = -1;
-    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false, no_band_tb = false, no_prebound = false, no_bound_order = false;
+    bool no_ckpt = false, no_bound = false, force_bound = false, no_quad = false, no_quad_pairs = false, no_band_tb = false, no_prebound = false, no_bound_order = false, no_skip_open = false;
     int force_period = 0;
     int arena_mb = 0;
     /* largest score seen in the last batch, per penalty set: sizes the rings of the next first pass */
@@ -306,6 +307,7 @@ extern "C" wfagpu_device_t *wfagpu_device_open(int dev)
     d->no_band_tb = env_int("WFAGPU_NO_BAND_TB", 0) != 0;
     d->no_prebound = env_int("WFAGPU_NO_PREBOUND", 0) != 0;
     d->no_bound_order = env_int("WFAGPU_NO_BOUND_ORDER", 0) != 0;
+    d->no_skip_open = env_int("WFAGPU_NO_SKIP_OPEN", 0) != 0;
     /* two scores per barrier interval: measured equal to one (22.9 vs 22.8 ms per 8192 x 10 kbp pairs) because the deeper
      * rings cost the fifth resident CTA; opt-in */
     d->no_quad_pairs = env_int("WFAGPU_QUAD_PAIRS", 0) == 0;
@@ -345,7 +347,7 @@ extern "C" void wfagpu_device_close_all(void)
             s.pool.release(); s.counters.release(); s.cells.release(); s.arena.release(); s.bound.release(); s.ck_off.release(); s.h_ck32.release(); s.h_bound.release(); s.h_retry.release();
             s.scratch.release(); s.steps.release(); s.band_lo.release(); s.gring.release(); s.slots.release(); s.text.release(); s.refs.release(); s.heads.release();
             s.h_text.release(); s.h_refs.release(); s.h_heads.release(); s.h_ascii.release();
-            s.h_pairs.release(); s.h_order.release(); s.h_out.release(); s.h_pool.release();
+            s.h_pairs.release(); s.h_order.release(); s.h_seed.release(); s.h_out.release(); s.h_pool.release();
             s.h_counters.release(); s.h_cells.release(); s.h_steps.release();
             for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
             if (s.ev_tab) cudaEventDestroy(s.ev_tab);
@@ -759,6 +761,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
      * without hints and a call after a batch of another kind all run at the speed of a well-hinted one.  Costs one
      * host round trip per pass (bounds back: 4 bytes per pair). */
     int d_p99 = 0;                           /* 99 % of the bounded pairs finish below this score (0 = unknown) */
+    size_t n_seed = 0;                       /* pairs at the end of the order list that skip this pass (no bound within the budget) */
     if (first_pass && !have_bounds && plan.band <= 0 && !ascii && !d->no_bound && !d->no_prebound && n_items == s.n) {
         bool pays = d->force_bound;
         if (!pays) {
@@ -799,17 +802,32 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
             have_bounds = true;
             if (order_dev == s.order.p && !d->no_bound_order) {
                 /* longest first by the pair's own bound (work ~ bound^2): the queue's tail is made of the cheapest pairs
-                 * (counting sort, descending; pairs without a bound first).  The order list was uploaded before the sync. */
+                 * (counting sort, descending).  Pairs the bound pass could not bound within this budget go to the end of
+                 * the list and straight to the re-dispatch tier: their first pass would run to the end of the budget for
+                 * nothing (a pair flagged for the byte-compare kernel stays: the wavefront kernel routes it).
+                 * The order list was uploaded before the sync. */
                 std::vector<uint32_t> &cnt = s.bound_count;
-                cnt.assign((size_t)d_full + 1, 0u);
-                for (size_t i = 0; i < s.n; ++i) cnt[(size_t)std::min(std::max(s.h_bound.p[i], 0), d_full - 1)] += 1;
-                uint32_t acc = 0;
-                for (int b = d_full - 1; b >= 0; --b) { const uint32_t c0 = cnt[(size_t)b]; cnt[(size_t)b] = acc; acc += c0; }
+                cnt.assign((size_t)d_full + 2, 0u);
+                auto key_of = [&](int32_t b) -> size_t {
+                    if (b == 0x7fffffff) return (size_t)d_full;              /* flagged: first */
+                    if (b >= d_full - 1) return (size_t)d_full + 1;          /* open: last (descending order below) */
+                    return (size_t)std::max(b, 0);
+                };
+                size_t n_open = 0;
                 for (size_t i = 0; i < s.n; ++i) {
-                    const size_t b = (size_t)std::min(std::max(s.h_bound.p[i], 0), d_full - 1);
-                    s.h_order.p[cnt[b]++] = (uint32_t)i;
+                    const size_t k = key_of(s.h_bound.p[i]);
+                    cnt[k] += 1;
+                    n_open += (k == (size_t)d_full + 1);
                 }
+                uint32_t acc = 0;
+                for (int b = d_full; b >= 0; --b) { const uint32_t c0 = cnt[(size_t)b]; cnt[(size_t)b] = acc; acc += c0; }
+                cnt[(size_t)d_full + 1] = acc;
+                for (size_t i = 0; i < s.n; ++i) s.h_order.p[cnt[key_of(s.h_bound.p[i])]++] = (uint32_t)i;
                 CK(cudaMemcpyAsync(s.order.p, s.h_order.p, s.n * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+                if (n_open > 0 && !d->no_skip_open) {
+                    n_seed = n_open;
+                    n_items = s.n - n_open;
+                }
             }
             if (!bv.empty()) {
                 const size_t k99 = (bv.size() - 1) - (bv.size() - 1) / 100;
@@ -973,7 +991,15 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     if (s.pool.ensure(pool_need, true, s.stream)) return -1;
 
     tr.mark("buffers");
-    CK(cudaMemsetAsync(s.counters.p + CTR_RETRY, 0, sizeof(uint32_t), s.stream));
+    if (n_seed > 0) {
+        /* the re-dispatch list starts with the pairs that skip this pass */
+        if (s.h_seed.ensure(1)) return -1;
+        s.h_seed.p[0] = (uint32_t)n_seed;
+        CK(cudaMemcpyAsync(s.counters.p + CTR_RETRY, s.h_seed.p, sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(retry_dev, s.order.p + n_items, n_seed * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s.stream));
+    } else {
+        CK(cudaMemsetAsync(s.counters.p + CTR_RETRY, 0, sizeof(uint32_t), s.stream));
+    }
 
     KernelParams kp{};
     kp.packed = s.packed.p;
@@ -1166,6 +1192,7 @@ extern "C" int wfagpu_device_align(wfagpu_device_t *d, int slot, size_t n, const
     s.stats.ascii_pairs = 0;
     CK(cudaMemsetAsync(s.counters.p, 0, CTR_WORDS * sizeof(uint32_t), s.stream));
     CK(cudaMemsetAsync(s.cells.p, 0, sizeof(unsigned long long), s.stream));
+    CK(cudaMemsetAsync(s.out.p, 0, n * sizeof(wfagpu_pair_out_t), s.stream));   /* a pair may skip the first pass: no stale record */
     CK(cudaEventRecord(s.ev[2], s.stream));
     PackParams pp{s.ascii.p, s.packed.p, s.pairs.p, (uint32_t)n};
     launch_pack(pp, s.stream);

@@ -1724,7 +1724,7 @@ __global__ void __launch_bounds__(256) wfa_bound_kernel(const __grid_constant__ 
         if (pos >= p.n_items) break;
         const uint32_t idx = p.order[pos];
         const wfagpu_pair_t pr = p.pairs[idx];
-        if (pr.flags & WFAGPU_PAIR_HAS_N) { if (lane == 0) p.bound[idx] = Dlaunch; continue; }
+        if (pr.flags & WFAGPU_PAIR_HAS_N) { if (lane == 0) p.bound[idx] = 0x7fffffff; continue; }    /* byte-compare pair: no bound, and the host can tell */
         const int plen = (int)pr.plen, tlen = (int)pr.tlen, kt = tlen - plen;
         const uint32_t *const Pw = p.packed + pr.p_word;
         const uint32_t *const Tw = p.packed + pr.t_word;
