@@ -152,12 +152,15 @@ def test_host_and_device_cigar_text_agree(oracle, monkeypatch):
                                      {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_CK_PERIOD": "31"},
                                      {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_NO_HINT": "1"},
                                      {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_ARENA_MB": "8"},
+                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_NO_PREBOUND": "1"}, {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_NO_SKIP_OPEN": "1"},
+                                     {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_NO_BOUND_ORDER": "1"},
                                      {"WFAGPU_QUAD_MIN": "1"}, {"WFAGPU_QUAD_MIN": "1", "WFAGPU_FORCE_BOUND": "1", "WFAGPU_CK_PERIOD": "31"},
                                      {"WFAGPU_QUAD_MIN": "1", "WFAGPU_QUAD_PAIRS": "1"},
                                      {"WFAGPU_QUAD_MIN": "1", "WFAGPU_QUAD_PAIRS": "1", "WFAGPU_FORCE_BOUND": "1", "WFAGPU_CK_PERIOD": "7"},
                                      {"WFAGPU_NO_QUAD": "1"}, {"WFAGPU_NO_BAND_TB": "1"}, {"WFAGPU_FORCE_LARGE": "1"}, {"WFAGPU_FORCE_LARGE": "1", "WFAGPU_NO_QUAD": "1"}])
 def test_kernel_variants_are_bit_exact(variant):
-    # per-pair score bounds on/off, ring snapshots vs decision bytes, snapshot periods, four diagonals per thread (forced for
+    # per-pair score bounds on/off, bounds before or inside the pass, queue in bound or length order, unbounded pairs skipping
+    # the first pass or not, ring snapshots vs decision bytes, snapshot periods, four diagonals per thread (forced for
     # every ring width with WFAGPU_QUAD_MIN=1) vs one, one or two scores per barrier interval, the large tier: one result
     import subprocess, sys as _sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

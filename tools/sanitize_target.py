@@ -26,6 +26,7 @@ FAMILIES = {
     "large":      (12, 600, 0.08, 200, True, -1, 0, {"WFAGPU_FORCE_LARGE": "1"}),
     "ascii":      (24, 400, 0.05, 100, True, -1, 0, {}),
     "redispatch": (32, 800, 0.10, 40, True, -1, 0, {}),
+    "prebound":   (48, 800, 0.10, 230, True, -1, 0, {"WFAGPU_FORCE_BOUND": "1", "WFAGPU_QUAD_MIN": "1"}),   # bounds first: bound-ordered queue, unbounded pairs skip the first pass
     "quad_pairs": (40, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_QUAD_PAIRS": "1", "WFAGPU_QUAD_MIN": "1"}),      # two scores per barrier interval
     "one_diag":   (24, 1000, 0.10, 400, True, -1, 0, {"WFAGPU_NO_QUAD": "1"}),         # one diagonal per thread (the -c path)
     "workers":    (96, 600, 0.06, 200, True, -1, 0, {"WFAGPU_DEVICES": "0,0"}),        # two workers, one GPU
