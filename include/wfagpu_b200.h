@@ -122,8 +122,10 @@ void wfagpu_device_close_all(void);
  * per device let the host overlap batch c+1's copies with batch c's kernels):
  *   upload    H2D of the batch's ASCII (pairs[i].*_ascii are offsets into
  *             `ascii`), pair descriptors and the longest-first schedule;
- *   align     pack kernel + alignment kernel (+ traceback); may be repeated on a
- *             resident batch; asynchronous;
+ *   align     pack kernel, score-bound kernel, alignment kernel (+ traceback, CIGAR text); may be
+ *             repeated on a resident batch.  Returns with the alignment kernels queued; for long
+ *             reads it first waits for the bound kernel (the rings of the pass are sized from the
+ *             batch's own bounds: 4 bytes per pair come back to the host), the rest is asynchronous;
  *   download  waits, finishes over-budget / non-ACGT pairs on the GPU
  *             (re-dispatch with a doubled budget, byte-compare kernel) and copies
  *             out[i] and the packed op streams back (`*ops` points into pinned
