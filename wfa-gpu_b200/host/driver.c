@@ -500,10 +500,10 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
             const size_t floor_pairs = (size_t)10 * (size_t)(sms > 0 ? sms : 148);
             first = chunk / (size_t)ramp;
             if (first < floor_pairs) first = floor_pairs;
-        } else if (ramp > 1 && job.n_chunks >= (size_t)2 * (size_t)ndev && (span / job.n) * chunk >= ((size_t)16 << 20)) {
+        } else if (ramp > 1 && opt.band <= 0 && job.n_chunks >= (size_t)2 * (size_t)ndev && (span / job.n) * chunk >= ((size_t)16 << 20)) {
             /* two big chunks per worker (long reads): half a chunk first -- its upload (and the bound pass the launch
              * waits for) is the exposed part of the call (measured on B200, 8192 x 10 kbp: 4096 + 4096 -> 31.6 ms,
-             * 2048 + 4096 + 2048 -> 30.7 ms) */
+             * 2048 + 4096 + 2048 -> 30.7 ms; the banded launch does not wait for anything: 28.8 against 29.8 ms) */
             const int sms = get_cuda_SM_count(devs[0]);
             const size_t floor_pairs = (size_t)10 * (size_t)(sms > 0 ? sms : 148);
             if (chunk / 2 >= floor_pairs) first = chunk / 2;
