@@ -106,6 +106,7 @@ typedef struct {
     size_t n_chunks;
     size_t next_from;       /* guarded by mu: first pair not handed out yet */
     size_t first_chunk;     /* size of the first chunk of every worker (ramp-up: its upload is not hidden) */
+    int nworkers;           /* host threads (one per device-list entry) that share the stream of chunks */
     pthread_mutex_t mu;
     bool failed;
     bool verbose;
@@ -148,6 +149,17 @@ static bool take_chunk(worker_t *w, size_t *from, size_t *n)
     if (!j->failed && j->next_from < j->n) {
         size_t want = j->chunk;
         if (!w->first_taken) { want = j->first_chunk; w->first_taken = true; }
+        else if (j->nworkers > 1) {
+            /* the end of a shared stream: when there is not a full chunk left for every worker, the rest is split (never
+             * below a quarter chunk) so that no worker is left with a whole chunk while the others are done */
+            const size_t rem = j->n - j->next_from;
+            if (rem < want * (size_t)j->nworkers) {
+                size_t share = (rem + (size_t)j->nworkers - 1) / (size_t)j->nworkers;
+                const size_t least = j->chunk / 4 > 0 ? j->chunk / 4 : 1;
+                if (share < least) share = least;
+                if (share < want) want = share;
+            }
+        }
         *from = j->next_from;
         *n = (*from + want <= j->n) ? want : j->n - *from;
         j->next_from += *n;
@@ -528,6 +540,7 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     if (!job.host_cigar && !job.check && job.decode_threads > 4) job.decode_threads = 4;   /* only memcpy of finished text is left */
 
     const int nworkers = (size_t)ndev < job.n_chunks ? ndev : (int)job.n_chunks;
+    job.nworkers = nworkers;
     worker_t workers[MAX_DEVICES];
     pthread_t th[MAX_DEVICES];
     for (int i = 0; i < nworkers; ++i) { workers[i].job = &job; workers[i].dev = devs[i]; workers[i].first_taken = false; }
