@@ -41,8 +41,14 @@ struct DevBuf {
     int ensure(size_t n, bool keep = false, cudaStream_t s = 0)
     {
         if (n <= cap) return 0;
-        size_t ncap = std::max(n, cap + cap / 2);
+        /* geometric growth for small buffers only: a 40 GB arena that has to hold 41 GB must not become 60 GB */
+        size_t ncap = (n * sizeof(T) > ((size_t)256 << 20)) ? n : std::max(n, cap + cap / 2);
         T *np = nullptr;
+        if (!keep && p) {                      /* nothing to carry over: give the old buffer back first */
+            cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
         CK(cudaMalloc(&np, ncap * sizeof(T)));
         if (keep && p && cap) CK(cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
         if (keep) CK(cudaStreamSynchronize(s));
@@ -959,7 +965,7 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
     /* keep the arenas within a third of the free device memory: fewer, not smaller, groups
      * (decision bytes: one arena per resident group; snapshots: one per pair of a sub-launch) */
     size_t items_per_launch = n_items;
-    {
+    for (int attempt = 0;; ++attempt) {
         const size_t budget = arena_budget;
         if (c.ckpt || band_tb) {
             const size_t per_pair = (size_t)arena_units * sizeof(uint4) + (band_tb ? ((size_t)d_end + 1) * sizeof(int32_t) : 0) + 1;
@@ -970,6 +976,17 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
             const size_t max_ctas = std::max<size_t>(1, budget / per_group);
             if ((size_t)c.ctas > max_ctas) c.ctas = (int)max_ctas;
         }
+        /* an arena that has to grow is checked against the memory that is free right now (the budget may date from an
+         * emptier device: other slots, contexts and processes allocate too); the old arena is given back first */
+        const size_t want = (((c.ckpt || band_tb) ? items_per_launch : (size_t)c.ctas * c.groups_per_cta) * arena_units + 1);
+        if (want <= s.arena.cap || d->arena_mb > 0 || attempt >= 4) break;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); break; }
+        const size_t avail = free_b + s.arena.cap * sizeof(uint4);
+        const size_t spare = (size_t)2 << 30;                    /* text slots, op pool, staging of this pass */
+        if (want * sizeof(uint4) + spare <= avail) break;
+        arena_budget = std::max<size_t>((size_t)64 << 20, std::min(arena_budget / 2, avail > spare ? (avail - spare) / 2 : (size_t)0));
+        s.budget_cache = arena_budget;
     }
     const size_t groups = (size_t)c.ctas * c.groups_per_cta;
     const uint64_t gring_elems = c.global_ring ? (uint64_t)(c.A + 2 * c.E1) * (uint64_t)c.row_stride : 0;
