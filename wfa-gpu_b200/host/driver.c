@@ -104,7 +104,7 @@ typedef struct {
     bool pageable;          /* the caller's sequence buffer is not page-locked: stage every chunk */
     size_t n, chunk;
     size_t n_chunks;
-    size_t next_from;       /* guarded by mu: first pair not handed out yet */
+    size_t share_next[MAX_DEVICES], share_end[MAX_DEVICES];   /* guarded by mu: what is left of every worker's share */
     size_t first_chunk;     /* size of the first chunk of every worker (ramp-up: its upload is not hidden) */
     int nworkers;           /* host threads (one per device-list entry) that share the stream of chunks */
     pthread_mutex_t mu;
@@ -122,6 +122,7 @@ typedef struct {
 typedef struct {
     job_t *job;
     int dev;
+    int index;              /* which share of the stream is this worker's */
     bool first_taken;
 } worker_t;
 
@@ -141,29 +142,38 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* Every worker owns a contiguous share of the stream and walks it front to back (first chunk, chunks, remainder): equal
+ * GPUs finish together whatever the chunk sizes are.  A worker that runs dry takes half chunks from the back of the
+ * fullest share (a slower GPU, a device shared with another job). */
 static bool take_chunk(worker_t *w, size_t *from, size_t *n)
 {
     job_t *j = w->job;
     bool ok = false;
     pthread_mutex_lock(&j->mu);
-    if (!j->failed && j->next_from < j->n) {
-        size_t want = j->chunk;
-        if (!w->first_taken) { want = j->first_chunk; w->first_taken = true; }
-        else if (j->nworkers > 1) {
-            /* the end of a shared stream: when there is not a full chunk left for every worker, the rest is split (never
-             * below a quarter chunk) so that no worker is left with a whole chunk while the others are done */
-            const size_t rem = j->n - j->next_from;
-            if (rem < want * (size_t)j->nworkers) {
-                size_t share = (rem + (size_t)j->nworkers - 1) / (size_t)j->nworkers;
-                const size_t least = j->chunk / 4 > 0 ? j->chunk / 4 : 1;
-                if (share < least) share = least;
-                if (share < want) want = share;
+    if (!j->failed) {
+        size_t *next = &j->share_next[w->index], *end = &j->share_end[w->index];
+        if (*next < *end) {
+            size_t want = j->chunk;
+            if (!w->first_taken) { want = j->first_chunk; w->first_taken = true; }
+            *from = *next;
+            *n = (*end - *next < want) ? *end - *next : want;
+            *next += *n;
+            ok = true;
+        } else {
+            int best = -1;
+            size_t most = 0;
+            for (int k = 0; k < j->nworkers; ++k)
+                if (j->share_end[k] - j->share_next[k] > most) { most = j->share_end[k] - j->share_next[k]; best = k; }
+            if (best >= 0) {
+                size_t want = j->chunk / 2 > 0 ? j->chunk / 2 : 1;
+                if (want > most) want = most;
+                j->share_end[best] -= want;
+                *from = j->share_end[best];
+                *n = want;
+                w->first_taken = true;
+                ok = true;
             }
         }
-        *from = j->next_from;
-        *n = (*from + want <= j->n) ? want : j->n - *from;
-        j->next_from += *n;
-        ok = true;
     }
     pthread_mutex_unlock(&j->mu);
     return ok;
@@ -543,7 +553,17 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     job.nworkers = nworkers;
     worker_t workers[MAX_DEVICES];
     pthread_t th[MAX_DEVICES];
-    for (int i = 0; i < nworkers; ++i) { workers[i].job = &job; workers[i].dev = devs[i]; workers[i].first_taken = false; }
+    {
+        /* shares in whole chunks as far as possible, so that only the last worker's remainder is ragged */
+        const size_t per = (job.n + (size_t)nworkers - 1) / (size_t)nworkers;
+        size_t at = 0;
+        for (int i = 0; i < nworkers; ++i) {
+            job.share_next[i] = at;
+            at = (at + per < job.n && i + 1 < nworkers) ? at + per : job.n;
+            job.share_end[i] = at;
+        }
+    }
+    for (int i = 0; i < nworkers; ++i) { workers[i].job = &job; workers[i].dev = devs[i]; workers[i].index = i; workers[i].first_taken = false; }
     if (nworkers == 1) {
         worker_main(&workers[0]);
     } else {
