@@ -192,6 +192,13 @@ void wfagpu_set_devices(const char *spec);
 void wfagpu_plan_chunks(size_t n, size_t batch_size, int n_devices, size_t ascii_span,
                         size_t *chunk_out, size_t *n_chunks_out);
 
+/* How the chunks of a job are dealt to `nworkers` host threads (one per device-list entry): every worker owns a contiguous
+ * share [share_next[i], share_end[i]) and takes `want` pairs from its front; a worker whose share is used up takes `steal`
+ * pairs from the back of the fullest share.  Pure functions on the share table (the caller serialises); false = nothing left. */
+void wfagpu_plan_shares(size_t n, int nworkers, size_t *share_next, size_t *share_end);
+bool wfagpu_share_take(size_t *share_next, size_t *share_end, int nworkers, int index, size_t want, size_t steal,
+                       size_t *from, size_t *n);
+
 /* Host threads this library may use per call (result loop, staging copies, generators); 0 = OpenMP default.
  * torchrun pins OMP_NUM_THREADS=1 per rank: a rank that works alone can lift that. */
 void wfagpu_set_host_threads(int n);

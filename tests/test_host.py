@@ -298,6 +298,42 @@ def test_chunk_plan(lib):
     assert c * 20000 <= 3 * 2**30 and c * k >= 10**6
 
 
+def test_shares_of_a_multi_worker_stream(lib):
+    # in-library multi-GPU: every worker walks its own contiguous share (first chunk, chunks, remainder); a worker whose share
+    # is used up steals half chunks from the back of the fullest one.  Every pair is handed out exactly once.
+    import ctypes as C
+    def deal(n, workers, chunk, first, order):
+        nxt, end = (C.c_size_t * workers)(), (C.c_size_t * workers)()
+        lib.wfagpu_plan_shares(n, workers, nxt, end)
+        assert nxt[0] == 0 and end[workers - 1] == n and all(end[i] == nxt[i + 1] for i in range(workers - 1))
+        got, taken_first = [[] for _ in range(workers)], [False] * workers
+        frm, cnt = C.c_size_t(), C.c_size_t()
+        for w in order:
+            want = chunk if taken_first[w] else first
+            if lib.wfagpu_share_take(nxt, end, workers, w, want, chunk // 2, C.byref(frm), C.byref(cnt)):
+                got[w].append((frm.value, cnt.value))
+                taken_first[w] = True
+        covered = sorted(x for g in got for x in g)
+        at = 0
+        for f0, c0 in covered:
+            assert f0 == at and c0 > 0
+            at += c0
+        assert at == n
+        return got
+    # eight equal GPUs, 8 x 8192 pairs, chunks of 4096 with a 2048-pair first chunk: 2048 + 4096 + 2048 each, nothing stolen
+    got = deal(65536, 8, 4096, 2048, [w for _ in range(4) for w in range(8)])
+    assert all([c for _, c in g] == [2048, 4096, 2048] for g in got)
+    assert all(g[0][0] == 8192 * w for w, g in enumerate(got))
+    # one worker is four times faster than the other: it finishes its share and helps with half chunks from the back
+    got = deal(16384, 2, 4096, 4096, [0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0])
+    assert sum(c for _, c in got[0]) > sum(c for _, c in got[1]) > 0
+    assert any(f >= 8192 for f, _ in got[0])
+    # ragged: more workers than pairs, and a share that is not a multiple of the chunk
+    deal(5, 8, 4, 4, list(range(8)) * 2)
+    deal(10001, 3, 1024, 512, [0, 1, 2] * 8)
+    assert not lib.wfagpu_share_take((C.c_size_t * 2)(4, 9), (C.c_size_t * 2)(4, 9), 2, 5, 1, 1, C.byref(C.c_size_t()), C.byref(C.c_size_t()))
+
+
 def test_metadata_must_be_word_aligned(lib):
     import ctypes as C
     a = wfagpu.Aligner()

@@ -143,37 +143,54 @@ static double now_s(void)
 }
 
 /* Every worker owns a contiguous share of the stream and walks it front to back (first chunk, chunks, remainder): equal
- * GPUs finish together whatever the chunk sizes are.  A worker that runs dry takes half chunks from the back of the
- * fullest share (a slower GPU, a device shared with another job). */
+ * GPUs finish together whatever the chunk sizes are.  A worker that runs dry takes `steal` pairs from the back of the
+ * fullest share (a slower GPU, a device shared with another job).  Pure functions on the share table, so that the
+ * policy is testable without a GPU; the caller serialises. */
+void wfagpu_plan_shares(size_t n, int nworkers, size_t *share_next, size_t *share_end)
+{
+    if (nworkers < 1) return;
+    const size_t per = (n + (size_t)nworkers - 1) / (size_t)nworkers;
+    size_t at = 0;
+    for (int i = 0; i < nworkers; ++i) {
+        share_next[i] = at;
+        at = (at + per < n && i + 1 < nworkers) ? at + per : n;
+        share_end[i] = at;
+    }
+}
+
+bool wfagpu_share_take(size_t *share_next, size_t *share_end, int nworkers, int index, size_t want, size_t steal,
+                       size_t *from, size_t *n)
+{
+    if (index < 0 || index >= nworkers) return false;
+    if (share_next[index] < share_end[index]) {
+        const size_t left = share_end[index] - share_next[index];
+        *from = share_next[index];
+        *n = left < want ? left : (want > 0 ? want : 1);
+        share_next[index] += *n;
+        return true;
+    }
+    int best = -1;
+    size_t most = 0;
+    for (int k = 0; k < nworkers; ++k)
+        if (share_end[k] - share_next[k] > most) { most = share_end[k] - share_next[k]; best = k; }
+    if (best < 0) return false;
+    size_t take = steal > 0 ? steal : 1;
+    if (take > most) take = most;
+    share_end[best] -= take;
+    *from = share_end[best];
+    *n = take;
+    return true;
+}
+
 static bool take_chunk(worker_t *w, size_t *from, size_t *n)
 {
     job_t *j = w->job;
     bool ok = false;
     pthread_mutex_lock(&j->mu);
     if (!j->failed) {
-        size_t *next = &j->share_next[w->index], *end = &j->share_end[w->index];
-        if (*next < *end) {
-            size_t want = j->chunk;
-            if (!w->first_taken) { want = j->first_chunk; w->first_taken = true; }
-            *from = *next;
-            *n = (*end - *next < want) ? *end - *next : want;
-            *next += *n;
-            ok = true;
-        } else {
-            int best = -1;
-            size_t most = 0;
-            for (int k = 0; k < j->nworkers; ++k)
-                if (j->share_end[k] - j->share_next[k] > most) { most = j->share_end[k] - j->share_next[k]; best = k; }
-            if (best >= 0) {
-                size_t want = j->chunk / 2 > 0 ? j->chunk / 2 : 1;
-                if (want > most) want = most;
-                j->share_end[best] -= want;
-                *from = j->share_end[best];
-                *n = want;
-                w->first_taken = true;
-                ok = true;
-            }
-        }
+        const size_t want = w->first_taken ? j->chunk : j->first_chunk;
+        ok = wfagpu_share_take(j->share_next, j->share_end, j->nworkers, w->index, want, j->chunk / 2, from, n);
+        w->first_taken = true;
     }
     pthread_mutex_unlock(&j->mu);
     return ok;
@@ -553,16 +570,7 @@ static void run_job(char *buf, size_t buf_size, sequence_pair_t *meta, wfa_align
     job.nworkers = nworkers;
     worker_t workers[MAX_DEVICES];
     pthread_t th[MAX_DEVICES];
-    {
-        /* shares in whole chunks as far as possible, so that only the last worker's remainder is ragged */
-        const size_t per = (job.n + (size_t)nworkers - 1) / (size_t)nworkers;
-        size_t at = 0;
-        for (int i = 0; i < nworkers; ++i) {
-            job.share_next[i] = at;
-            at = (at + per < job.n && i + 1 < nworkers) ? at + per : job.n;
-            job.share_end[i] = at;
-        }
-    }
+    wfagpu_plan_shares(job.n, nworkers, job.share_next, job.share_end);
     for (int i = 0; i < nworkers; ++i) { workers[i].job = &job; workers[i].dev = devs[i]; workers[i].index = i; workers[i].first_taken = false; }
     if (nworkers == 1) {
         worker_main(&workers[0]);

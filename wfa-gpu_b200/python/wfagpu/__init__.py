@@ -92,7 +92,7 @@ EXPORTS = [
     "wfagpu_device_pack_only", "wfagpu_ops_to_cigar", "wfagpu_set_devices", "wfagpu_last_run_stats",
     "wfagpu_synth_add_pairs", "wfagpu_device_wait", "wfagpu_host_register", "wfagpu_host_unregister",
     "wfagpu_pairs_from_metadata", "wfagpu_reset_results", "wfagpu_read_seq_file", "wfagpu_read_fasta_files",
-    "wfagpu_check_result", "wfagpu_last_launch_ok", "wfagpu_plan_chunks",
+    "wfagpu_check_result", "wfagpu_last_launch_ok", "wfagpu_plan_chunks", "wfagpu_plan_shares", "wfagpu_share_take",
     "check_cigar_edit", "check_affine_distance", "wfagpu_cigar_append", "wfagpu_device_download_text",
     "recover_cigar", "wfagpu_unroll_cigar", "wfagpu_device_release", "wfagpu_device_rescore", "wfagpu_device_staging",
     "wfagpu_host_is_pinned", "wfagpu_host_alloc", "wfagpu_host_free", "wfagpu_reserve", "wfagpu_parse_devices",
@@ -134,6 +134,10 @@ def load():
     L.wfagpu_check_result.restype = C.c_bool
     L.wfagpu_plan_chunks.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, P(C.c_size_t), P(C.c_size_t)]
     L.wfagpu_plan_chunks.restype = None
+    L.wfagpu_plan_shares.argtypes = [C.c_size_t, C.c_int, P(C.c_size_t), P(C.c_size_t)]
+    L.wfagpu_plan_shares.restype = None
+    L.wfagpu_share_take.argtypes = [P(C.c_size_t), P(C.c_size_t), C.c_int, C.c_int, C.c_size_t, C.c_size_t, P(C.c_size_t), P(C.c_size_t)]
+    L.wfagpu_share_take.restype = C.c_bool
     L.wfagpu_reset_results.argtypes = [P(AlignerStruct)]
     L.wfagpu_reset_results.restype = None
     L.wfagpu_last_run_stats.argtypes = [P(RunStats)]
