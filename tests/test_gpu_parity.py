@@ -169,6 +169,22 @@ def test_kernel_variants_are_bit_exact(variant):
     assert pr.returncode == 0, pr.stdout[-3000:] + pr.stderr[-3000:]
 
 
+@pytest.mark.parametrize("pen,length,err,max_error", [((2, 250, 3), 400, 0.05, 2000), ((2, 250, 3), 3000, 0.03, 40), ((3, 120, 2), 2500, 0.04, 3000)])
+def test_penalties_whose_rings_do_not_fit_the_bound_kernel(oracle, pen, length, err, max_error):
+    # o + e = 253: the bound kernel's per-warp rings (A + 2 (e + 1) rows of 128 bytes, 8 warps) exceed the shared memory of an SM.
+    # No score bounds then: launch-bound pruning only, and over-budget pairs double their budget until they finish.
+    a = synth_aligner([(24, length, err, err)], 0xB2007700)
+    assert a.initialize_parameters(*pen)
+    a.options.compute_cigar = True
+    a.options.max_error = max_error
+    assert a.align()
+    assert a.run_stats()["failed_pairs"] == 0
+    for i in range(a.num_pairs):
+        p, t = a.pair(i)
+        r = oracle.align(p, t, *pen, 60000)
+        assert (a.error(i), a.cigar(i)) == (r["distance"], r["cigar"])
+
+
 def test_headline_batch_at_full_size(oracle, refcpu):
     # BASELINE's headline configuration at bench.py's full size (8192 x 10 kbp, 5 %, -e 3000, CIGAR),
     # checked through properties that do not need the oracle on every pair:

@@ -768,7 +768,8 @@ static int launch_pass(wfagpu_device *d, Slot &s, const wfagpu_plan_t &plan, int
      * host round trip per pass (bounds back: 4 bytes per pair). */
     int d_p99 = 0;                           /* 99 % of the bounded pairs finish below this score (0 = unknown) */
     size_t n_seed = 0;                       /* pairs at the end of the order list that skip this pass (no bound within the budget) */
-    if (first_pass && !have_bounds && plan.band <= 0 && !ascii && !d->no_bound && !d->no_prebound && n_items == s.n) {
+    if (first_pass && !have_bounds && plan.band <= 0 && !ascii && !d->no_bound && !d->no_prebound && n_items == s.n &&
+        bound_max_ctas_per_sm(std::max(plan.o + plan.e, plan.x) + 1, plan.e + 1, 8) >= 1) {   /* penalties whose rings fit the bound kernel */
         bool pays = d->force_bound;
         if (!pays) {
             const bool h = d_want < d_full && d->hint_mean > 0 && d->hint_dist > 0;
@@ -1268,6 +1269,7 @@ extern "C" int wfagpu_device_download(wfagpu_device_t *d, int slot, size_t n, wf
         *need = 0;
         const int kMaxSteps = d->max_steps_cap;
         int rc = run_bound_only(d, s, replan, kMaxSteps, s.retry[cur].p, pending);
+        if (rc == -2) return 0;                     /* the bound kernel does not fit these penalties: keep doubling */
         if (rc) return rc;
         if (s.h_bound.ensure(s.n + 1) || s.h_retry.ensure(pending + 1)) return -1;
         CK(cudaMemcpyAsync(s.h_bound.p, s.bound.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
