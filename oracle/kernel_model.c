@@ -451,3 +451,174 @@ int km_align_pair_ckpt(const char *pattern, int plen, const char *text, int tlen
     free(Mr); free(Ir); free(Dr);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Adaptive band on packed int16 quads (model of wfa_bandq_kernel + wfa_band_traceback_kernel).
+ *
+ * The heuristic is the reference's (window clip hi--/lo++, re-centre every `band` scores on the
+ * first diagonal with the smallest distance to the target, stale ring slots on null steps); what
+ * is modelled here is the kernel's DATA LAYOUT: a ring row stores the cells of its score's window
+ * at index k - base, base = lo rounded down to a multiple of four, in whole quads, cells outside
+ * the window as NULL; a read outside the stored part of a row (index < 0 or >= cells) yields NULL
+ * without touching memory; windows are records {lo, hi, base, cells} per slot (M rows, and one
+ * shared by the I and D rows); decisions come from the "which operand won" predicates of the max
+ * instructions (extend >= open, D >= X, max(D, X) >= I) and sit at byte k - base of the score's
+ * row; the backtrace reads the row base of every score from a table.  The rings are poisoned so
+ * that a read of a cell the kernel never wrote would show.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { int lo, hi, base, cells; } km_win_t;
+
+static inline int km_bq_get(const int16_t *row, km_win_t w, int k)
+{
+    const int idx = k - w.base;
+    return (idx >= 0 && idx < w.cells) ? row[idx] : KM_NULL;
+}
+
+int km_align_pair_bandq(const char *pattern, int plen, const char *text, int tlen,
+                        int x, int o, int e, const km_step_t *tab, int d_end, int band, int W,
+                        int with_bt, int *finished, int *distance,
+                        uint8_t *ops_out, int ops_cap, int *n_ops)
+{
+    const int A = imax(o + e, x) + 1;
+    const int oe = o + e;
+    const int RW = ((W + 3) & ~3) + 8;
+    int16_t *R[3];
+    for (int c = 0; c < 3; c++) {
+        R[c] = (int16_t *)malloc((size_t)A * RW * sizeof(int16_t));
+        for (long i = 0; i < (long)A * RW; i++) R[c][i] = 12345;           /* poison */
+    }
+    km_win_t *WM = (km_win_t *)malloc((size_t)A * sizeof(km_win_t));
+    km_win_t *WG = (km_win_t *)malloc((size_t)A * sizeof(km_win_t));
+    uint8_t *arena = with_bt ? (uint8_t *)malloc((size_t)d_end * RW) : NULL;
+    int *base_tab = (int *)malloc((size_t)d_end * sizeof(int));
+    if (arena) memset(arena, 0xEE, (size_t)d_end * RW);
+    /* every slot starts as the one-diagonal window [0, 0] holding NULL: one quad of NULLs at base 0 */
+    for (int s = 0; s < A; s++) {
+        WM[s] = (km_win_t){0, 0, 0, 4};
+        WG[s] = (km_win_t){0, 0, 0, 4};
+        for (int c = 0; c < 3; c++) for (int i = 0; i < 4; i++) R[c][s * RW + i] = KM_NULL;
+    }
+    R[0][0] = (int16_t)km_extend(text, pattern, tlen, plen, 0, 0);
+    const int kt = tlen - plen, kt_abs = kt < 0 ? -kt : kt;
+    int fin = 0, dist = 0, rc = 0;
+    if (kt == 0 && R[0][0] == tlen) {
+        fin = 1;
+    } else {
+        for (int d = 1; d < d_end; d++) {
+            const km_step_t st = tab[d];
+            const int sM = d % A;
+            if (st.kind == KM_KIND_NULL) continue;
+            const int sx = ((sM - x) % A + A) % A;
+            const km_win_t wx = WM[sx];
+            const int16_t *Mx = R[0] + sx * RW;
+            int16_t *Mc = R[0] + sM * RW;
+            int lo, hi, base;
+            if (st.kind == KM_KIND_M) {
+                lo = wx.lo; hi = wx.hi; base = wx.base;
+                const int nq = ((hi - base) >> 2) + 1;
+                for (int q = 0; q < nq; q++)
+                    for (int i = 0; i < 4; i++) {
+                        const int k = base + 4 * q + i;
+                        int m = (int16_t)(Mx[k - wx.base] + 1);           /* same base: always a stored cell */
+                        if (k < lo || k > hi) m = KM_NULL;
+                        if (m >= 0) m = km_extend(text, pattern, tlen, plen, k, m);
+                        Mc[k - base] = (int16_t)m;
+                    }
+                WM[sM] = wx;
+            } else {
+                const int so = ((sM - oe) % A + A) % A, sg = ((sM - e) % A + A) % A;
+                const km_win_t wo = WM[so], wg = WG[sg];
+                const int16_t *Mo = R[0] + so * RW, *Ie = R[1] + sg * RW, *De = R[2] + sg * RW;
+                int16_t *Ic = R[1] + sM * RW, *Dc = R[2] + sM * RW;
+                const int hi_ID = imax(wo.hi, wg.hi) + 1, lo_ID = imin(wo.lo, wg.lo) - 1;
+                hi = imax(wx.hi, hi_ID);
+                lo = imin(wx.lo, lo_ID);
+                const int excess = (hi - lo) - (W - 1);
+                if (excess > 0) { hi -= (excess + 1) >> 1; lo += excess >> 1; }
+                if ((wx.hi - wx.lo) >= W - 1 && (d % band) == 0) {
+                    long best_dt = 0x7fffffffL;
+                    int c = wx.lo, found = 0;
+                    for (int i = wx.lo; i < wx.hi; i++) {
+                        const int off = Mx[i - wx.base];
+                        if (off < 0) continue;
+                        const int left_v = (int16_t)(plen - (off - i)), left_h = (int16_t)(tlen - off);
+                        const long dt = imax(left_v, left_h);
+                        if (!found || dt < best_dt) { best_dt = dt; c = i; found = 1; }
+                    }
+                    if (!found || best_dt >= 2L * (tlen + plen)) c = wx.lo;
+                    lo = c - (W / 2);
+                    hi = lo + W - 1;
+                }
+                base = lo & ~3;
+                const km_win_t wc = {lo, hi, base, ((hi - base) | 3) + 1};
+                if (wc.cells > RW) { rc = -1; break; }
+                const int nq = ((hi - base) >> 2) + 1;
+                uint8_t *row = with_bt ? arena + (size_t)d * RW : NULL;
+                /* all reads of a score happen before its writes land in another slot: sM is never its own source */
+                for (int q = 0; q < nq; q++)
+                    for (int i = 0; i < 4; i++) {
+                        const int k = base + 4 * q + i;
+                        const int io = km_bq_get(Mo, wo, k - 1), ie = km_bq_get(Ie, wg, k - 1);
+                        const int dopen = km_bq_get(Mo, wo, k + 1), dext = km_bq_get(De, wg, k + 1);
+                        const int X = (int16_t)(km_bq_get(Mx, wx, k) + 1);
+                        const int pI = ie >= io, pD = dext >= dopen;
+                        int I = (int16_t)(imax(ie, io) + 1), D = imax(dext, dopen);
+                        const int pa = D >= X, T = imax(D, X), pb = T >= I;
+                        int M = imax(T, I);
+                        if (k < lo || k > hi) { I = KM_NULL; D = KM_NULL; M = KM_NULL; }
+                        if (M >= 0) M = km_extend(text, pattern, tlen, plen, k, M);
+                        Ic[k - base] = (int16_t)I; Dc[k - base] = (int16_t)D; Mc[k - base] = (int16_t)M;
+                        if (with_bt) row[k - base] = (uint8_t)(pI | (pD << 1) | ((pb ? (pa ? 3 : 2) : 1) << 2));
+                    }
+                WM[sM] = wc;
+                WG[sM] = wc;
+                base_tab[d] = base;
+            }
+            if (kt_abs <= d) {
+                const int t = (kt >= lo && kt <= hi) ? Mc[kt - base] : KM_NULL;
+                if (t == tlen) { fin = 1; dist = d; break; }
+                if (t > tlen) break;
+            }
+        }
+    }
+    *finished = fin;
+    *distance = fin ? dist : 0;
+    *n_ops = 0;
+    if (fin && with_bt && dist > 0 && rc == 0) {
+        int cd = dist, ck = kt, comp = 0, cnt = 0;
+#define KM_RES_M(dd) do { while ((dd) > 0 && tab[dd].kind == KM_KIND_NULL) (dd) -= A; } while (0)
+#define KM_RES_G(dd) do { while ((dd) > 0 && tab[dd].kind != KM_KIND_MDI) (dd) -= A; } while (0)
+        while (!(comp == 0 && cd == 0)) {
+            if (cd < 0 || cnt >= ops_cap) { rc = -1; break; }
+            const km_step_t st = tab[cd];
+            int op;
+            if (comp == 0 && st.kind == KM_KIND_M) {
+                op = 2; cd -= x; KM_RES_M(cd);
+            } else {
+                if (st.kind != KM_KIND_MDI) { rc = -1; break; }
+                const int ii = ck - base_tab[cd];
+                if (ii < 0 || ii >= RW) { rc = -1; break; }
+                const uint8_t dec = arena[(size_t)cd * RW + ii];
+                if (dec == 0xEE) { rc = -1; break; }                       /* a byte the forward pass never wrote */
+                if (comp == 0) {
+                    op = 2;
+                    const int mop = (dec >> 2) & 3;
+                    if (mop == 2) { cd -= x; KM_RES_M(cd); }
+                    else if (mop == 1) comp = 1;
+                    else comp = 2;
+                } else if (comp == 1) {
+                    op = 1; ck -= 1;
+                    if (dec & 1) { cd -= e; KM_RES_G(cd); } else { cd -= oe; KM_RES_M(cd); comp = 0; }
+                } else {
+                    op = 3; ck += 1;
+                    if (dec & 2) { cd -= e; KM_RES_G(cd); } else { cd -= oe; KM_RES_M(cd); comp = 0; }
+                }
+            }
+            ops_out[cnt++] = (uint8_t)op;
+        }
+        *n_ops = cnt;
+    }
+    for (int c = 0; c < 3; c++) free(R[c]);
+    free(WM); free(WG); free(arena); free(base_tab);
+    return rc;
+}

@@ -61,6 +61,9 @@ class Oracle:
         L.km_align_pair_ckpt.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 3 + [
             C.POINTER(KmStep), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
             C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_long)]
+        L.km_align_pair_bandq.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 3 + [
+            C.POINTER(KmStep)] + [C.c_int] * 4 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int)]
+        L.km_align_pair_bandq.restype = C.c_int
         L.km_align_pair.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int] + [C.c_int] * 3 + [
             C.POINTER(KmStep), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
             C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_long)]
@@ -132,6 +135,25 @@ class Oracle:
         if fin.value:
             cg = self.decode_ops(pattern, text, dist.value, list(ops[: nops.value])[::-1])
         return dict(finished=bool(fin.value), distance=dist.value, cigar=cg, recomputed=rec.value)
+
+    def model_align_bandq(self, pattern, text, x, o, e, max_steps, band, window, cigar=True):
+        """CPU model of wfa_bandq_kernel's data layout (rows at k - base in whole quads, reads outside the stored part of a
+        row are NULL, window records, decisions from the max predicates) + wfa_band_traceback_kernel."""
+        p, t = _b(pattern), _b(text)
+        max_dist = max_steps * (max(x, o + e) + 2) + 16
+        tab = (KmStep * (max_dist + 1))()
+        words = C.c_uint64()
+        d_end = self.L.km_build_steps(x, o, e, max_steps, max_dist, tab, C.byref(words))
+        fin, dist, nops = C.c_int(), C.c_int(), C.c_int()
+        cap = 2 * d_end + 16
+        ops = (C.c_uint8 * cap)()
+        rc = self.L.km_align_pair_bandq(p, len(p), t, len(t), x, o, e, tab, d_end, band, window, int(cigar),
+                                        C.byref(fin), C.byref(dist), ops, cap, C.byref(nops))
+        assert rc == 0, "banded model failed (row capacity or a decision byte that was never written)"
+        cg = None
+        if fin.value and cigar:
+            cg = self.decode_ops(pattern, text, dist.value, list(ops[: nops.value])[::-1])
+        return dict(finished=bool(fin.value), distance=dist.value, cigar=cg)
 
     # -- CPU model of the B200 kernel's algorithm ------------------------------
     def model_align(self, pattern, text, x, o, e, max_steps, cigar=True, n_cap=None):

@@ -64,3 +64,25 @@ def test_model_budget_rule_equals_oracle(oracle, pen):
             assert m["finished"] == r["finished"]
             if r["finished"]:
                 assert m["distance"] == r["distance"]
+
+
+@pytest.mark.parametrize("pen,band,window", [((2, 3, 1), 10, 64), ((2, 3, 1), 25, 128), ((2, 3, 1), 5, 32), ((2, 3, 1), 25, 30),
+                                             ((4, 6, 2), 25, 96), ((5, 3, 2), 10, 64), ((1, 0, 1), 7, 48), ((3, 5, 2), 50, 128)])
+def test_banded_quad_layout_equals_oracle(oracle, pen, band, window):
+    # wfa_bandq_kernel's data layout (rows at k - base in whole quads with NULL outside the window, reads outside the stored
+    # part of a row yield NULL, window records shared by the I and D rows, decisions from "which operand won") against the
+    # restatement of the reference's banded kernels: same finished flag, score and CIGAR -- also where the band loses the
+    # alignment, where windows jump at a re-centre, and with null steps (gcd > 1)
+    pairs = make_pairs(13, [(600, 0.08, 14), (1500, 0.04, 5), (300, 0.15, 12), (90, 0.05, 10), (0, 0, 1)])
+    pairs += [("", "ACGT"), ("ACGT", ""), ("ACGT", "ACGT"), ("A", "C"), ("ACGT" * 60, "ACGT" * 60 + "T" * 45),
+              ("GATTACA" * 40 + "C" * 77, "GATTACA" * 40)]
+    n_fin = 0
+    for p, t in pairs:
+        for budget in (1500, 60):
+            r = oracle.align(p, t, *pen, budget, band=band, window=window)
+            m = oracle.model_align_bandq(p, t, *pen, budget, band, window)
+            assert m["finished"] == r["finished"]
+            if r["finished"]:
+                assert (m["distance"], m["cigar"]) == (r["distance"], r["cigar"])
+                n_fin += 1
+    assert n_fin > len(pairs) // 2
